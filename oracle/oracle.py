@@ -1,0 +1,211 @@
+"""CPU fp64 restatement of raft::distance::pairwise_distance / fusedL2NN (TEST INFRASTRUCTURE).
+
+Header: see oracle/__init__.py ("parity unpinned").  Every function cites the reference
+file:line it follows; where the reference source was deleted upstream the citation is the
+surviving evidence listed in SURVEY.md section 8(a).
+"""
+from __future__ import annotations
+
+import enum
+import numpy as np
+
+__all__ = [
+    "DistanceType", "pairwise_distance", "fused_l2_nn", "row_norm_sq", "argmin_op",
+    "row_argmin", "compare_approx", "match_approx", "make_blobs", "EXPANDED", "UNEXPANDED",
+    "pack_minloc", "unpack_minloc",
+]
+
+
+class DistanceType(enum.IntEnum):
+    """raft::distance::DistanceType (enum values: SURVEY.md 8(a1); type name proven by
+    cpp/include/raft/stats/silhouette_score.cuh:45)."""
+    L2Expanded = 0
+    L2SqrtExpanded = 1
+    CosineExpanded = 2
+    L1 = 3
+    L2Unexpanded = 4
+    L2SqrtUnexpanded = 5
+    InnerProduct = 6
+    Linf = 7
+    Canberra = 8
+    LpUnexpanded = 9
+    CorrelationExpanded = 10
+    JaccardExpanded = 11
+    HellingerExpanded = 12
+    Haversine = 13
+    BrayCurtis = 14
+    JensenShannon = 15
+    HammingUnexpanded = 16
+    KLDivergence = 17
+    RusselRaoExpanded = 18
+    DiceExpanded = 19
+    Precomputed = 100
+
+
+EXPANDED = (DistanceType.L2Expanded, DistanceType.L2SqrtExpanded, DistanceType.CosineExpanded,
+            DistanceType.CorrelationExpanded, DistanceType.InnerProduct)
+UNEXPANDED = (DistanceType.L1, DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded,
+              DistanceType.Linf, DistanceType.Canberra, DistanceType.LpUnexpanded)
+
+
+def row_norm_sq(x: np.ndarray) -> np.ndarray:
+    """Squared L2 row norm, fp64 (spec: cpp/include/raft/linalg/norm.cuh:50-58, L2Norm =
+    sum of squares, naive check cpp/tests/linalg/norm.cu:42-66)."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.einsum("ij,ij->i", x, x)
+
+
+def _block(x64, y64, metric, p):
+    if metric in (DistanceType.L2Expanded, DistanceType.L2SqrtExpanded,
+                  DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded):
+        # mathematically identical; fp64 expanded form is exact enough to be the oracle,
+        # but use the difference form for robustness to cancellation.
+        xn = np.einsum("ij,ij->i", x64, x64)
+        yn = np.einsum("ij,ij->i", y64, y64)
+        d = xn[:, None] + yn[None, :] - 2.0 * (x64 @ y64.T)
+        # fp64 cancellation error is ~1e-16*|x|^2, far below the 1e-4 bar; clamp like the
+        # reference epilogue does ("clamp <0 -> 0").
+        np.maximum(d, 0.0, out=d)
+        if metric in (DistanceType.L2SqrtExpanded, DistanceType.L2SqrtUnexpanded):
+            np.sqrt(d, out=d)
+        return d
+    if metric == DistanceType.InnerProduct:
+        return x64 @ y64.T
+    if metric == DistanceType.CosineExpanded:
+        xn = np.sqrt(np.einsum("ij,ij->i", x64, x64))
+        yn = np.sqrt(np.einsum("ij,ij->i", y64, y64))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return 1.0 - (x64 @ y64.T) / (xn[:, None] * yn[None, :])
+    if metric == DistanceType.CorrelationExpanded:
+        # 1 - (k*sum(xy) - sum(x)sum(y)) / sqrt((k*sum(x^2)-sum(x)^2)(k*sum(y^2)-sum(y)^2))
+        # (SURVEY.md 8(a3)); computed on centred rows, which is the same quantity.
+        xc = x64 - x64.mean(axis=1, keepdims=True)
+        yc = y64 - y64.mean(axis=1, keepdims=True)
+        xn = np.sqrt(np.einsum("ij,ij->i", xc, xc))
+        yn = np.sqrt(np.einsum("ij,ij->i", yc, yc))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return 1.0 - (xc @ yc.T) / (xn[:, None] * yn[None, :])
+    # unexpanded metrics: SURVEY.md 8(a4)
+    diff = x64[:, None, :] - y64[None, :, :]
+    if metric == DistanceType.L1:
+        return np.abs(diff).sum(axis=2)
+    if metric == DistanceType.Linf:
+        return np.abs(diff).max(axis=2) if diff.shape[2] else np.zeros(diff.shape[:2])
+    if metric == DistanceType.Canberra:
+        den = np.abs(x64)[:, None, :] + np.abs(y64)[None, :, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(den == 0.0, 0.0, np.abs(diff) / den)   # 0/0 -> 0
+        return t.sum(axis=2)
+    if metric == DistanceType.LpUnexpanded:
+        return (np.abs(diff) ** p).sum(axis=2) ** (1.0 / p)
+    raise ValueError(f"metric {metric!r} not on the hot path")
+
+
+def pairwise_distance(x, y, metric=DistanceType.L2Expanded, metric_arg: float = 2.0,
+                      block: int = 256) -> np.ndarray:
+    """dist[i,j] = metric(x_i, y_j); x:[m,k], y:[n,k] row-major -> [m,n] fp64.
+
+    Follows raft::distance::pairwise_distance (call shape:
+    cpp/include/raft/stats/detail/silhouette_score.cuh:205-206; semantics SURVEY.md 8(a2-a4)).
+    Inputs are taken at their own precision (fp32/fp16) and promoted to fp64."""
+    metric = DistanceType(metric)
+    x64 = np.ascontiguousarray(x, dtype=np.float64)
+    y64 = np.ascontiguousarray(y, dtype=np.float64)
+    assert x64.ndim == 2 and y64.ndim == 2 and x64.shape[1] == y64.shape[1]
+    m, n = x64.shape[0], y64.shape[0]
+    out = np.empty((m, n), dtype=np.float64)
+    if metric in EXPANDED + (DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded):
+        block = max(block, 2048)
+    for i0 in range(0, m, block):
+        for j0 in range(0, n, block):
+            out[i0:i0 + block, j0:j0 + block] = _block(
+                x64[i0:i0 + block], y64[j0:j0 + block], metric, float(metric_arg))
+    return out
+
+
+def argmin_op(a, b):
+    """raft::argmin_op on (key, value) pairs: cpp/include/raft/core/operators.hpp:187-194."""
+    if (b[1] < a[1]) or ((a[1] == b[1]) and (b[0] < a[0])):
+        return b
+    return a
+
+
+def row_argmin(mat: np.ndarray) -> np.ndarray:
+    """raft::matrix::argmin: cpp/include/raft/matrix/argmin.cuh:25-37 (ties -> smaller
+    index, same as np.argmin's first-occurrence rule)."""
+    return np.argmin(np.asarray(mat), axis=1).astype(np.int32)
+
+
+def fused_l2_nn(x, y, sqrt: bool = False, block: int = 4096):
+    """out[i] = (argmin_j, min_j) ||x_i - y_j||^2 (or its sqrt), ties -> smaller j.
+
+    Follows raft::distance::fusedL2NN[MinReduce] (tie-break law
+    cpp/include/raft/core/operators.hpp:187-194).  Returns (idx int32[m], val fp64[m])."""
+    x64 = np.ascontiguousarray(x, dtype=np.float64)
+    y64 = np.ascontiguousarray(y, dtype=np.float64)
+    m, n = x64.shape[0], y64.shape[0]
+    best_v = np.full(m, np.inf)
+    best_i = np.zeros(m, dtype=np.int64)
+    for j0 in range(0, n, block):
+        d = _block(x64, y64[j0:j0 + block], DistanceType.L2Expanded, 2.0)
+        loc = np.argmin(d, axis=1)
+        v = d[np.arange(m), loc]
+        upd = v < best_v                     # strict: earlier (smaller) index wins ties
+        best_v = np.where(upd, v, best_v)
+        best_i = np.where(upd, loc + j0, best_i)
+    if sqrt:
+        best_v = np.sqrt(best_v)
+    return best_i.astype(np.int32), best_v
+
+
+def compare_approx(a, b, eps):
+    """raft::CompareApprox: cpp/tests/test_utils.h:31-45 (relative when diff > eps, else
+    absolute).  Vectorised; returns a boolean array."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    diff = np.abs(a - b)
+    m = np.maximum(np.abs(a), np.abs(b))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(diff > eps, diff / m, diff)
+    both_nan = np.isnan(a) & np.isnan(b)     # CompareApproxNaN, test_utils.h:47-63
+    return (ratio <= eps) | both_nan
+
+
+def match_approx(actual, expected, eps):
+    ok = compare_approx(actual, expected, eps)
+    if ok.all():
+        return True, ""
+    bad = np.argwhere(~ok)
+    i = tuple(bad[0])
+    return False, (f"{(~ok).sum()} mismatches of {ok.size}; first at {i}: "
+                   f"actual={np.asarray(actual)[i]!r} expected={np.asarray(expected)[i]!r}")
+
+
+def pack_minloc(val_f32: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """Host model of the packed min-loc key the multi-GPU exchange reduces with MIN
+    (SURVEY.md 8(e)): high 32 bits = float bits remapped so that signed-integer order equals
+    float order, low 32 bits = index.  int64 MIN == (min value, then smaller index)."""
+    bits = np.asarray(val_f32, dtype=np.float32).view(np.int32).astype(np.int64)
+    s = np.where(bits < 0, bits ^ 0x7FFFFFFF, bits)
+    return (s << 32) | (np.asarray(idx).astype(np.int64) & 0xFFFFFFFF)
+
+
+def unpack_minloc(key: np.ndarray):
+    key = np.asarray(key, dtype=np.int64)
+    idx = (key & 0xFFFFFFFF).astype(np.int32)
+    s = (key >> 32).astype(np.int64)
+    bits = np.where(s < 0, s ^ 0x7FFFFFFF, s).astype(np.int32)
+    return bits.view(np.float32), idx
+
+
+def make_blobs(n_rows, n_cols, n_clusters=5, cluster_std=1.0, box=(-10.0, 10.0), seed=1234,
+               centers=None, dtype=np.float32):
+    """Isotropic Gaussian blobs like raft::random::make_blobs
+    (cpp/include/raft/random/make_blobs.cuh:124-140 defaults: 5 clusters, std 1, centre box
+    [-10,10]).  Same distribution, not the same bit pattern."""
+    rng = np.random.default_rng(seed)
+    if centers is None:
+        centers = rng.uniform(box[0], box[1], size=(n_clusters, n_cols))
+    labels = rng.integers(0, centers.shape[0], size=n_rows)
+    data = centers[labels] + cluster_std * rng.standard_normal((n_rows, n_cols))
+    return data.astype(dtype), labels.astype(np.int32), centers

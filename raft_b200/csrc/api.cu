@@ -1,0 +1,417 @@
+// C-ABI entry points (include/raft_b200.h) and host-side dispatch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/raft_b200.h"
+#include "expanded_tc.cuh"
+#include "prep.cuh"
+#include "unexpanded_simt.cuh"
+
+namespace b2d {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+#define B2D_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(B2D_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptor encode through the driver entry point (no link-time libcuda dependency, so the
+// library still loads -- and reports a clean error -- on a machine without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// packed operand [rows][nkb*64] fp16, box = 64 x box_rows, SWIZZLE_128B
+static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int nkb, int box_rows)
+{
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2]    = {static_cast<cuuint64_t>(nkb) * 64, static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(nkb) * 128};
+  cuuint32_t box[2]     = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return B2D_OK;
+}
+
+static int device_sms(int* sms, int* cc_major)
+{
+  int dev = 0;
+  B2D_CUDA(cudaGetDevice(&dev));
+  B2D_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  B2D_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace layout of the tensor-core path
+struct TcWorkspace {
+  __half* xop;
+  __half* yop;
+  float2* xvec;
+  float2* yvec;
+  long long* keys;
+  size_t bytes;
+};
+
+static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool with_keys)
+{
+  const int nkb = static_cast<int>((k + 31) / 32);
+  size_t off    = 0;
+  auto take     = [&](size_t b) {
+    size_t o = off;
+    off += align_up(b, 1024);
+    return o;
+  };
+  char* c = static_cast<char*>(base);
+  TcWorkspace w;
+  // xvec and keys come first so that their offsets depend on m only (b2d_fused_l2_nn_finalize
+  // finds |x_i|^2 again without knowing n or k)
+  w.xvec = reinterpret_cast<float2*>(c + take(static_cast<size_t>(m) * 8));
+  w.keys = reinterpret_cast<long long*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
+  w.yvec = reinterpret_cast<float2*>(c + take(static_cast<size_t>(n) * 8));
+  w.xop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(m) * nkb * 128));
+  w.yop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(n) * nkb * 128));
+  w.bytes = off;
+  return w;
+}
+
+static bool is_expanded(int metric)
+{
+  return metric == B2D_L2Expanded || metric == B2D_L2SqrtExpanded || metric == B2D_CosineExpanded ||
+         metric == B2D_CorrelationExpanded || metric == B2D_InnerProduct;
+}
+static bool is_unexpanded(int metric)
+{
+  return metric == B2D_L1 || metric == B2D_L2Unexpanded || metric == B2D_L2SqrtUnexpanded ||
+         metric == B2D_Linf || metric == B2D_Canberra || metric == B2D_LpUnexpanded;
+}
+
+template <typename T>
+static int launch_prep(cudaStream_t s, const void* src, int64_t rs, int64_t cs, int64_t rows, int64_t k,
+                       __half* op, float2* vec, const float* ext, int mode, int side, int center)
+{
+  if (rows == 0) return B2D_OK;
+  PrepParams p;
+  p.src = src; p.rs = rs; p.cs = cs; p.rows = rows; p.k = static_cast<int>(k);
+  p.nkb = static_cast<int>((k + 31) / 32); p.op = op; p.vec = vec; p.ext_norm_sq = ext;
+  p.mode = mode; p.side = side; p.center = center;
+  const int64_t blocks = (rows + 7) / 8;
+  prep_rows_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+template <bool kRes, int kEpi>
+static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid)
+{
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  const size_t smem = tc_smem_bytes(kRes);
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem));
+  });
+  // the attribute is per device; set it again cheaply when several devices are in use
+  if (attr_err == cudaSuccess)
+    attr_err = cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem));
+  B2D_CUDA(attr_err);
+  expanded_tc_kernel<kRes, kEpi><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi)
+{
+  int sms = 0, cc = 0;
+  int rc  = device_sms(&sms, &cc);
+  if (rc) return rc;
+  if (cc != 10) return fail(B2D_ERR_CUDA, "raft_b200 requires an sm_100 (B200) device; found cc major " + std::to_string(cc));
+  p.nkb     = static_cast<int>((k + 31) / 32);
+  p.tiles_m = static_cast<int>((p.m + TC_BM - 1) / TC_BM);
+  p.tiles_n = static_cast<int>((p.n + TC_BN - 1) / TC_BN);
+  int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  int64_t chunk = total / (static_cast<int64_t>(sms) * 6);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 32) chunk = 32;
+  if (chunk > p.tiles_m) chunk = p.tiles_m;
+  p.chunk    = static_cast<int>(chunk);
+  p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
+  p.n_items  = static_cast<int64_t>(p.tiles_n) * p.chunks_m;
+  p.xvec     = w.xvec;
+  p.yvec     = w.yvec;
+  if (p.n_items == 0) return B2D_OK;
+  CUtensorMap ma, mb;
+  rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN);
+  if (rc) return rc;
+  const int grid      = static_cast<int>(p.n_items < sms ? p.n_items : sms);
+  const bool resident = p.nkb <= TC_MAX_RES_KB;
+  if (resident) {
+    return epi == EPI_STORE ? launch_tc_inst<true, EPI_STORE>(s, ma, mb, p, grid)
+                            : launch_tc_inst<true, EPI_MINLOC>(s, ma, mb, p, grid);
+  }
+  return epi == EPI_STORE ? launch_tc_inst<false, EPI_STORE>(s, ma, mb, p, grid)
+                          : launch_tc_inst<false, EPI_MINLOC>(s, ma, mb, p, grid);
+}
+
+template <int kMetric>
+static int launch_ux_inst(cudaStream_t s, const UxParams& p, int64_t tiles)
+{
+  cudaError_t e = cudaFuncSetAttribute(unexpanded_simt_kernel<kMetric>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       UX_SMEM_BYTES);
+  B2D_CUDA(e);
+  unexpanded_simt_kernel<kMetric><<<static_cast<unsigned>(tiles), UX_THREADS, UX_SMEM_BYTES, s>>>(p);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void row_norm_kernel(float* out, const float* x, int64_t ldx, int64_t rows, int k, int type, int do_sqrt)
+{
+  const int lane  = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* row = x + r * ldx;
+  double acc = 0.0;
+  float mx   = 0.f;
+  for (int t = lane; t < k; t += 32) {
+    const float v = __ldg(row + t);
+    if (type == B2D_L0PseudoNorm) acc += (v != 0.f) ? 1.0 : 0.0;
+    else if (type == B2D_L1Norm) acc += fabs(static_cast<double>(v));
+    else if (type == B2D_L2Norm) acc += static_cast<double>(v) * v;
+    else mx = fmaxf(mx, fabsf(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+    double v = (type == B2D_LinfNorm) ? static_cast<double>(mx) : acc;
+    if (do_sqrt) v = sqrt(v);
+    out[r] = static_cast<float>(v);
+  }
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" {
+
+int b2d_version(void) { return 100; }
+const char* b2d_last_error(void) { return g_err.c_str(); }
+
+size_t b2d_pairwise_workspace_bytes(int metric, int dtype, int64_t m, int64_t n, int64_t k)
+{
+  if (dtype != B2D_F32 && dtype != B2D_F16) return static_cast<size_t>(-1);
+  if (m < 0 || n < 0 || k < 0) return static_cast<size_t>(-1);
+  if (is_unexpanded(metric)) return dtype == B2D_F32 ? 0 : static_cast<size_t>(-1);
+  if (!is_expanded(metric)) return static_cast<size_t>(-1);
+  return tc_layout(nullptr, m, n, k, false).bytes;
+}
+
+int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, int64_t ldx, const void* y,
+                          int64_t ldy, float* dist, int64_t ldd, int64_t m, int64_t n, int64_t k,
+                          int row_major, float metric_arg, void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
+  if (m == 0 || n == 0) return B2D_OK;
+  if (!x || !y || !dist) return fail(B2D_ERR_INVALID_ARG, "null x / y / dist");
+  if (m > 0x7fffffffll * 128 || n > 0x7fffffffll || k > (1 << 24)) return fail(B2D_ERR_INVALID_ARG, "extent too large");
+  if (row_major) {
+    if (ldx < k || ldy < k || ldd < n) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than the row length");
+  } else {
+    if (ldx < m || ldy < n || ldd < m) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than the column length");
+  }
+  if (!is_expanded(metric) && !is_unexpanded(metric))
+    return fail(B2D_ERR_UNSUPPORTED, "metric " + std::to_string(metric) + " is not on the B200 distance path");
+  if (dtype != B2D_F32 && dtype != B2D_F16) return fail(B2D_ERR_UNSUPPORTED, "dtype");
+  if (metric == B2D_LpUnexpanded && !(metric_arg > 0.f)) return fail(B2D_ERR_INVALID_ARG, "LpUnexpanded needs p > 0");
+
+  // Fortran order: D^T (row-major [n,m]) = metric(y_j, x_i); all metrics here are symmetric.
+  const void *xa = x, *ya = y;
+  int64_t ma = m, na = n;
+  int64_t xrs, xcs, yrs, ycs;
+  if (row_major) { xrs = ldx; xcs = 1; yrs = ldy; ycs = 1; }
+  else { xa = y; ya = x; ma = n; na = m; xrs = 1; xcs = ldy; yrs = 1; ycs = ldx; }
+
+  if (is_expanded(metric)) {
+    const size_t need = tc_layout(nullptr, ma, na, k, false).bytes;
+    if (!workspace || workspace_bytes < need)
+      return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+    TcWorkspace w = tc_layout(workspace, ma, na, k, false);
+    int mode = PREP_L2, center = 0, post = POST_NONE;
+    if (metric == B2D_L2Expanded) { post = POST_CLAMP; }
+    else if (metric == B2D_L2SqrtExpanded) { post = POST_CLAMP_SQRT; }
+    else if (metric == B2D_CosineExpanded) { mode = PREP_COSINE; }
+    else if (metric == B2D_CorrelationExpanded) { mode = PREP_COSINE; center = 1; }
+    else { mode = PREP_INNER; }
+    int rc;
+    if (dtype == B2D_F32) {
+      rc = launch_prep<float>(s, xa, xrs, xcs, ma, k, w.xop, w.xvec, nullptr, mode, 0, center);
+      if (rc) return rc;
+      rc = launch_prep<float>(s, ya, yrs, ycs, na, k, w.yop, w.yvec, nullptr, mode, 1, center);
+    } else {
+      rc = launch_prep<__half>(s, xa, xrs, xcs, ma, k, w.xop, w.xvec, nullptr, mode, 0, center);
+      if (rc) return rc;
+      rc = launch_prep<__half>(s, ya, yrs, ycs, na, k, w.yop, w.yvec, nullptr, mode, 1, center);
+    }
+    if (rc) return rc;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd; p.post = post;
+    p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy) ? 1 : 0;
+    p.vec_ok    = (reinterpret_cast<uintptr_t>(dist) % 16 == 0 && ldd % 4 == 0) ? 1 : 0;
+    return launch_tc(s, w, p, k, EPI_STORE);
+  }
+
+  if (dtype != B2D_F32) return fail(B2D_ERR_UNSUPPORTED, "unexpanded metrics take fp32 inputs");
+  UxParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const float*>(xa); p.y = static_cast<const float*>(ya); p.dist = dist;
+  p.xrs = xrs; p.xcs = xcs; p.yrs = yrs; p.ycs = ycs; p.ldd = ldd; p.m = ma; p.n = na; p.k = static_cast<int>(k);
+  p.vec_x = (xcs == 1 && xrs % 4 == 0 && k % 4 == 0 && reinterpret_cast<uintptr_t>(xa) % 16 == 0) ? 1 : 0;
+  p.vec_y = (ycs == 1 && yrs % 4 == 0 && k % 4 == 0 && reinterpret_cast<uintptr_t>(ya) % 16 == 0) ? 1 : 0;
+  p.p = metric_arg; p.inv_p = 1.f / metric_arg;
+  p.tiles_n = static_cast<int>((na + UX_BN - 1) / UX_BN);
+  const int64_t tiles = ((ma + UX_BM - 1) / UX_BM) * p.tiles_n;
+  int cc = 0, sms = 0;
+  int rc = device_sms(&sms, &cc);
+  if (rc) return rc;
+  if (cc != 10) return fail(B2D_ERR_CUDA, "raft_b200 requires an sm_100 (B200) device");
+  switch (metric) {
+    case B2D_L1: return launch_ux_inst<UX_L1>(s, p, tiles);
+    case B2D_L2Unexpanded: return launch_ux_inst<UX_L2>(s, p, tiles);
+    case B2D_L2SqrtUnexpanded: return launch_ux_inst<UX_L2SQRT>(s, p, tiles);
+    case B2D_Linf: return launch_ux_inst<UX_LINF>(s, p, tiles);
+    case B2D_Canberra: return launch_ux_inst<UX_CANBERRA>(s, p, tiles);
+    default: return launch_ux_inst<UX_LP>(s, p, tiles);
+  }
+}
+
+size_t b2d_fused_l2_nn_workspace_bytes(int64_t m, int64_t n, int64_t k)
+{
+  if (m < 0 || n < 0 || k < 0) return static_cast<size_t>(-1);
+  return tc_layout(nullptr, m, n, k, true).bytes;
+}
+
+int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                         const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int64_t idx_offset,
+                         int init_keys, void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
+  if (m == 0) return B2D_OK;
+  if (!keys || !x || (n > 0 && !y)) return fail(B2D_ERR_INVALID_ARG, "null keys / x / y");
+  if (ldx < k || ldy < k) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than k");
+  if (n + idx_offset > 0xFFFFFFFFll || idx_offset < 0) return fail(B2D_ERR_INVALID_ARG, "index range exceeds 32 bits");
+  const size_t need = tc_layout(nullptr, m, n, k, true).bytes;
+  if (!workspace || workspace_bytes < need)
+    return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+  TcWorkspace w = tc_layout(workspace, m, n, k, true);
+  if (init_keys) {
+    minloc_init_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), m);
+    B2D_CUDA(cudaGetLastError());
+  }
+  int rc = launch_prep<float>(s, x, ldx, 1, m, k, w.xop, w.xvec, xn, PREP_L2, 0, 0);
+  if (rc) return rc;
+  if (n == 0) return B2D_OK;
+  rc = launch_prep<float>(s, y, ldy, 1, n, k, w.yop, w.yvec, yn, PREP_L2, 1, 0);
+  if (rc) return rc;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
+  return launch_tc(s, w, p, k, EPI_MINLOC);
+}
+
+int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys, int64_t m, int do_sqrt,
+                             const void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
+  if (m == 0) return B2D_OK;
+  if (!out || !keys || !workspace) return fail(B2D_ERR_INVALID_ARG, "null out / keys / workspace");
+  if (workspace_bytes < static_cast<size_t>(m) * 8) return fail(B2D_ERR_WORKSPACE, "workspace too small");
+  TcWorkspace w = tc_layout(const_cast<void*>(workspace), m, 0, 0, true);
+  minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
+    reinterpret_cast<KvpIF*>(out), reinterpret_cast<const long long*>(keys), w.xvec, m, do_sqrt, 0);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                    const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int do_sqrt, int init_out,
+                    void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
+  if (m == 0) return B2D_OK;
+  if (!out) return fail(B2D_ERR_INVALID_ARG, "null out");
+  const size_t need = tc_layout(nullptr, m, n, k, true).bytes;
+  if (!workspace || workspace_bytes < need)
+    return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  TcWorkspace w = tc_layout(workspace, m, n, k, true);
+  int rc = b2d_fused_l2_nn_keys(stream, reinterpret_cast<int64_t*>(w.keys), x, ldx, y, ldy, xn, yn, m, n, k, 0, 1,
+                                workspace, workspace_bytes);
+  if (rc) return rc;
+  minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
+    reinterpret_cast<KvpIF*>(out), w.keys, w.xvec, m, do_sqrt, init_out ? 0 : 1);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k, int norm_type,
+                 int do_sqrt)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows < 0 || k < 0 || ldx < k) return fail(B2D_ERR_INVALID_ARG, "bad extents");
+  if (norm_type < B2D_L0PseudoNorm || norm_type > B2D_LinfNorm) return fail(B2D_ERR_INVALID_ARG, "norm type");
+  if (rows == 0) return B2D_OK;
+  if (!out || !x) return fail(B2D_ERR_INVALID_ARG, "null out / x");
+  row_norm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(out, x, ldx, rows, static_cast<int>(k),
+                                                                        norm_type, do_sqrt);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+}  // extern "C"

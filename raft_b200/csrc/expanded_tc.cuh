@@ -1,0 +1,361 @@
+// K1 / K3: expanded-form metrics on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the pair loop of raft::distance::pairwise_distance for L2Expanded / L2SqrtExpanded /
+// CosineExpanded / CorrelationExpanded / InnerProduct and of raft::distance::fusedL2NN
+// (SURVEY.md 8(a2),(a3),(a5); the reference's last implementation was a CUTLASS 3xTF32 mma.sync
+// kernel, CHANGELOG.md:1443,1140 -- this is not a port of it).
+//
+// Numerics: fp32 inputs are pre-split (prep.cuh) into fp16 hi/lo with a power-of-two row scale;
+// acc = hi*hi + hi*lo + lo*hi accumulates in fp32 in TMEM (products of fp16 pairs are exact in
+// fp32), i.e. ~22 significant bits per operand -- fp32-grade, same idea as the reference's 3xTF32
+// but at the 2x higher kind::f16 rate and with 4 B/element staged instead of 8.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   TMA producer      cp.async.bulk.tensor 2-D, SWIZZLE_128B, mbarrier complete_tx
+//   warp 1   MMA issuer        one thread issues tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16
+//   warps 2-5 epilogue         tcgen05.ld 32x32b (thread == output row), fused epilogue in
+//                              registers, then either a swizzled smem transpose + full-line
+//                              coalesced streaming stores (pairwise) or a per-row running
+//                              min / arg-min + one packed 64-bit atomicMin per row per tile (NN).
+// Two 128x256 fp32 accumulators fill TMEM's 512 columns: MMA of tile t+1 overlaps the epilogue of
+// tile t.  Work item = (256-column block of y, run of 128-row tiles of x).  With k <= 128 the
+// y block (both halves, all of K: <= 128 KB) stays resident in shared memory for the whole run and
+// only x tiles stream through a 4-stage ring, which cuts L2->SM operand traffic to ~21 B/clk/SM;
+// for larger k both operands stream per k-block.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ptx.cuh"
+
+namespace b2d {
+
+constexpr int TC_BM          = 128;
+constexpr int TC_BN          = 256;
+constexpr int TC_A_BYTES     = TC_BM * 128;  // one k-block of A: 128 rows x 128 B
+constexpr int TC_B_BYTES     = TC_BN * 128;  // one k-block of B: 256 rows x 128 B
+constexpr int TC_STAGES      = 4;
+constexpr int TC_MAX_RES_KB  = 4;            // resident-B variant: k <= 128
+constexpr int TC_THREADS     = 192;
+constexpr int TC_STG_FLOATS  = 32 * 32;      // per epilogue warp transpose buffer
+
+enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1 };
+enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
+
+struct TcParams {
+  int64_t m, n;
+  int nkb;                // k-blocks of 32 source columns
+  int tiles_m, tiles_n;   // ceil(m/128), ceil(n/256)
+  int chunk;              // m-tiles per work item
+  int chunks_m;           // ceil(tiles_m/chunk)
+  int64_t n_items;        // tiles_n * chunks_m
+  const float2* xvec;     // [m] (a.x, a.y)
+  const float2* yvec;     // [n] (b.x, b.y)
+  // EPI_STORE
+  float* dist;
+  int64_t ldd;
+  int post;
+  int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
+  int vec_ok;             // 16-byte aligned rows -> st.v4
+  // EPI_MINLOC
+  long long* keys;        // [m] packed (ordered float bits << 32 | index)
+  int64_t idx_offset;
+};
+
+__host__ __device__ inline size_t tc_smem_bytes(bool resident)
+{
+  size_t op = resident ? (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES * TC_A_BYTES
+                       : (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES);
+  return 1024 /*align slack*/ + op + 4 * TC_STG_FLOATS * 4 + TC_BN * 8 + 256;
+}
+
+// float -> int whose signed order equals the float order
+__device__ __forceinline__ int ordered_bits(float v)
+{
+  int b = __float_as_int(v);
+  return b < 0 ? (b ^ 0x7FFFFFFF) : b;
+}
+
+template <bool kResident, int kEpi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                   const __grid_constant__ CUtensorMap tmap_b, const TcParams p)
+{
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  // carve
+  uint8_t* b_base = smem;                                                     // resident slabs or per-stage B
+  uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES * TC_B_BYTES);
+  float* stg      = reinterpret_cast<float*>(a_base + TC_STAGES * TC_A_BYTES);
+  float2* colvec  = reinterpret_cast<float2*>(stg + 4 * TC_STG_FLOATS);
+  uint64_t* bars  = reinterpret_cast<uint64_t*>(colvec + TC_BN);
+  uint64_t* afull = bars;                  // [TC_STAGES]
+  uint64_t* aempty = bars + TC_STAGES;     // [TC_STAGES]
+  uint64_t* bfull = bars + 2 * TC_STAGES;  // [TC_MAX_RES_KB]
+  uint64_t* bempty = bfull + TC_MAX_RES_KB;
+  uint64_t* tfull = bempty + TC_MAX_RES_KB;  // [2]
+  uint64_t* tempty = tfull + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { ptx::mbar_init(&afull[i], 1); ptx::mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < TC_MAX_RES_KB; ++i) { ptx::mbar_init(&bfull[i], 1); ptx::mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = p.nkb;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_last();
+      uint32_t a_it = 0, it_local = 0;
+      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+        const int n_blk = static_cast<int>(item % p.tiles_n);
+        const int ch    = static_cast<int>(item / p.tiles_n);
+        const int mt0   = ch * p.chunk;
+        const int mt1   = min(mt0 + p.chunk, p.tiles_m);
+        for (int mt = mt0; mt < mt1; ++mt) {
+          for (int kb = 0; kb < nkb; ++kb, ++a_it) {
+            if (kResident && mt == mt0) {
+              ptx::mbar_wait(&bempty[kb], (it_local & 1) ^ 1);
+              ptx::mbar_expect_tx(&bfull[kb], TC_B_BYTES);
+              ptx::tma_load_2d(b_base + kb * TC_B_BYTES, &tmap_b, &bfull[kb], kb * 64, n_blk * TC_BN, pol);
+            }
+            const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
+            ptx::mbar_wait(&aempty[s], ph ^ 1);
+            ptx::mbar_expect_tx(&afull[s], kResident ? TC_A_BYTES : TC_A_BYTES + TC_B_BYTES);
+            ptx::tma_load_2d(a_base + s * TC_A_BYTES, &tmap_a, &afull[s], kb * 64, mt * TC_BM, pol);
+            if (!kResident)
+              ptx::tma_load_2d(b_base + s * TC_B_BYTES, &tmap_b, &afull[s], kb * 64, n_blk * TC_BN, pol);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(TC_BM, TC_BN);
+      uint32_t a_it = 0, t_it = 0, it_local = 0;
+      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+        const int ch  = static_cast<int>(item / p.tiles_n);
+        const int mt0 = ch * p.chunk;
+        const int mt1 = min(mt0 + p.chunk, p.tiles_m);
+        for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
+          const uint32_t as = t_it & 1, aph = (t_it >> 1) & 1;
+          ptx::mbar_wait(&tempty[as], aph ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_addr = tmem_base + as * TC_BN;
+          for (int kb = 0; kb < nkb; ++kb, ++a_it) {
+            if (kResident && mt == mt0) ptx::mbar_wait(&bfull[kb], it_local & 1);
+            const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
+            ptx::mbar_wait(&afull[s], ph);
+            ptx::tc_fence_after();
+            const uint32_t a_addr = ptx::smem_u32(a_base + s * TC_A_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(b_base + (kResident ? kb : (int)s) * TC_B_BYTES);
+            const uint64_t da = ptx::umma_desc_sw128(a_addr);
+            const uint64_t db = ptx::umma_desc_sw128(b_addr);
+            // byte offsets inside the 128-B swizzled row (>>4 in descriptor units):
+            //   hi k[0,16) +0, hi k[16,32) +32, lo k[0,16) +64, lo k[16,32) +96
+            // lo*hi and hi*lo first (small terms), hi*hi last.
+            ptx::mma_f16_ss(d_addr, da + 4, db + 0, idesc, kb > 0 ? 1u : 0u);  // lo0 * hi0
+            ptx::mma_f16_ss(d_addr, da + 6, db + 2, idesc, 1u);                // lo1 * hi1
+            ptx::mma_f16_ss(d_addr, da + 0, db + 4, idesc, 1u);                // hi0 * lo0
+            ptx::mma_f16_ss(d_addr, da + 2, db + 6, idesc, 1u);                // hi1 * lo1
+            ptx::mma_f16_ss(d_addr, da + 0, db + 0, idesc, 1u);                // hi0 * hi0
+            ptx::mma_f16_ss(d_addr, da + 2, db + 2, idesc, 1u);                // hi1 * hi1
+            ptx::mma_commit(&aempty[s]);
+            if (kResident && mt == mt1 - 1) ptx::mma_commit(&bempty[kb]);
+          }
+          ptx::mma_commit(&tfull[as]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue warps ===============================
+    const int q        = warp & 3;            // TMEM lane quarter this warp may read
+    const int ew       = warp - 2;            // 0..3, staging buffer id
+    const int et       = threadIdx.x - 64;    // 0..127
+    const int row_in_t = q * 32 + lane;
+    float* my_stg      = stg + ew * TC_STG_FLOATS;
+    uint32_t t_it      = 0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int n_blk = static_cast<int>(item % p.tiles_n);
+      const int ch    = static_cast<int>(item / p.tiles_n);
+      const int mt0   = ch * p.chunk;
+      const int mt1   = min(mt0 + p.chunk, p.tiles_m);
+      // column pairs of this y block (shared by every tile of the item)
+      ptx::bar_sync(1, 128);
+      for (int c = et; c < TC_BN; c += 128) {
+        const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + c;
+        float2 cv;
+        if (gj < p.n) cv = __ldg(&p.yvec[gj]);
+        else cv = make_float2(0.f, kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f);
+        colvec[c] = cv;
+      }
+      ptx::bar_sync(1, 128);
+
+      for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
+        const uint32_t as = t_it & 1, aph = (t_it >> 1) & 1;
+        const int64_t gi  = static_cast<int64_t>(mt) * TC_BM + row_in_t;
+        float2 rv         = make_float2(0.f, 0.f);
+        if (gi < p.m) rv = __ldg(&p.xvec[gi]);
+        ptx::mbar_wait(&tfull[as], aph);
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * TC_BN;
+
+        float best_v = __int_as_float(0x7f800000);
+        int best_j   = 0x7fffffff;
+
+#pragma unroll 1
+        for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_addr + chunk * 32, r);
+          ptx::tmem_ld_wait();
+          if (chunk == TC_BN / 32 - 1) {
+            // accumulator fully drained into registers: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+          }
+          const int cbase = chunk * 32;
+          if (kEpi == EPI_STORE) {
+            const int64_t gj0 = static_cast<int64_t>(n_blk) * TC_BN + cbase;
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float4 cv = *reinterpret_cast<const float4*>(&colvec[cbase + c]);
+              float v0 = fmaf(__uint_as_float(r[c]) * rv.x, cv.x, rv.y + cv.y);
+              float v1 = fmaf(__uint_as_float(r[c + 1]) * rv.x, cv.z, rv.y + cv.w);
+              if (p.post != POST_NONE) {
+                v0 = fmaxf(v0, 0.f);
+                v1 = fmaxf(v1, 0.f);
+                if (p.diag_zero) {
+                  if (gi == gj0 + c) v0 = 0.f;
+                  if (gi == gj0 + c + 1) v1 = 0.f;
+                }
+                if (p.post == POST_CLAMP_SQRT) {
+                  asm("sqrt.approx.f32 %0, %1;" : "=f"(v0) : "f"(v0));
+                  asm("sqrt.approx.f32 %0, %1;" : "=f"(v1) : "f"(v1));
+                }
+              }
+              r[c]     = __float_as_uint(v0);
+              r[c + 1] = __float_as_uint(v1);
+            }
+            // transpose through shared memory (16-byte chunks XOR-swizzled by row: conflict-free
+            // both ways) so that every global store instruction writes whole 128-byte row segments
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float4 v = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
+                                     __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+              *reinterpret_cast<float4*>(my_stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = v;
+            }
+            __syncwarp();
+            const int c4 = lane & 7;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr      = it * 4 + (lane >> 3);
+              const float4 v    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+              const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
+              const int64_t gj  = gj0 + c4 * 4;
+              if (gi2 < p.m) {
+                float* dst = p.dist + gi2 * p.ldd + gj;
+                if (p.vec_ok && gj + 3 < p.n) {
+                  ptx::st_global_cs_v4(dst, v);
+                } else {
+                  if (gj < p.n) ptx::st_global_cs(dst, v.x);
+                  if (gj + 1 < p.n) ptx::st_global_cs(dst + 1, v.y);
+                  if (gj + 2 < p.n) ptx::st_global_cs(dst + 2, v.z);
+                  if (gj + 3 < p.n) ptx::st_global_cs(dst + 3, v.w);
+                }
+              }
+            }
+            __syncwarp();
+          } else {
+            // running (min, argmin) over ascending column index; strict '<' keeps the smallest
+            // index on ties (raft::argmin_op, cpp/include/raft/core/operators.hpp:187-194)
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float4 cv = *reinterpret_cast<const float4*>(&colvec[cbase + c]);
+              const float v0  = fmaf(__uint_as_float(r[c]) * rv.x, cv.x, cv.y);
+              const float v1  = fmaf(__uint_as_float(r[c + 1]) * rv.x, cv.z, cv.w);
+              if (v0 < best_v) { best_v = v0; best_j = cbase + c; }
+              if (v1 < best_v) { best_v = v1; best_j = cbase + c + 1; }
+            }
+          }
+        }
+        if (kEpi == EPI_MINLOC) {
+          if (gi < p.m && best_j != 0x7fffffff) {
+            const long long gj  = static_cast<long long>(n_blk) * TC_BN + best_j + p.idx_offset;
+            const long long key = (static_cast<long long>(ordered_bits(best_v)) << 32) | (gj & 0xFFFFFFFFll);
+            atomicMin(&p.keys[gi], key);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helper kernels for the NN path
+
+__global__ void minloc_init_kernel(long long* keys, int64_t m)
+{
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < m) keys[i] = 0x7FFFFFFFFFFFFFFFll;
+}
+
+struct KvpIF {
+  int key;
+  float value;
+};
+
+// packed key -> raft::KeyValuePair<int,float>{argmin, min distance}; adds the row-constant
+// |x_i|^2 that the pair loop leaves out, clamps at 0, optional sqrt.
+__global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const float2* xvec,
+                                       int64_t m, int do_sqrt, int merge_existing)
+{
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long key = keys[i];
+  int s               = static_cast<int>(key >> 32);
+  int bits            = s < 0 ? (s ^ 0x7FFFFFFF) : s;
+  float v             = __int_as_float(bits);
+  float d             = fmaxf(xvec[i].y + v, 0.f);
+  if (do_sqrt) d = sqrtf(d);
+  KvpIF o;
+  o.key   = static_cast<int>(key & 0xFFFFFFFFll);
+  o.value = d;
+  if (key == 0x7FFFFFFFFFFFFFFFll) {  // no candidate (n == 0)
+    o.key   = 0x7fffffff;
+    o.value = __int_as_float(0x7f7fffff);
+  }
+  if (merge_existing) {
+    // initOutBuffer == false: reduce into what the caller already has (argmin_op)
+    KvpIF e = out[i];
+    if ((e.value < o.value) || (e.value == o.value && e.key < o.key)) o = e;
+  }
+  out[i] = o;
+}
+
+}  // namespace b2d

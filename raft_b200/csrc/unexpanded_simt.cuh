@@ -1,0 +1,171 @@
+// K2: unexpanded metrics (L1, L2Unexpanded, L2SqrtUnexpanded, Linf, Canberra, LpUnexpanded) --
+// not bilinear, so no tensor-core form: a register-tiled FP32 kernel.
+//
+// 128x128 output tile per CTA, 256 threads, 8x8 outputs per thread, k-blocks of 32 floats staged
+// in shared memory as 128-byte rows whose 16-byte chunks are XOR-swizzled by (row & 7) -- the
+// same pattern TMA's SWIZZLE_128B produces -- so both the cooperative 16-byte loads into smem
+// and the LDS.128 reads along k are bank-conflict free.  Global reads are 128-byte coalesced
+// float4 loads when the rows are 16-byte aligned and k % 4 == 0, scalar otherwise (any row /
+// column stride, zero-filled tails: what the reference's Contractions_NT loader guaranteed,
+// cpp/include/raft/linalg/detail/contractions.cuh:186-193).  The next k-block is fetched into
+// registers while the current one is consumed (software pipelining, double-buffered smem).
+// Bound: FP32 pipe (>= 2 lane-ops per pair-element), not HBM -- see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace b2d {
+
+constexpr int UX_BM = 128, UX_BN = 128, UX_KB = 32, UX_THREADS = 256;
+constexpr int UX_SMEM_BYTES = 2 * (UX_BM + UX_BN) * UX_KB * 4;
+
+enum UxMetric : int { UX_L1 = 0, UX_L2 = 1, UX_L2SQRT = 2, UX_LINF = 3, UX_CANBERRA = 4, UX_LP = 5 };
+
+struct UxParams {
+  const float* x;
+  const float* y;
+  float* dist;
+  int64_t xrs, xcs, yrs, ycs;  // element strides
+  int64_t ldd;
+  int64_t m, n;
+  int k;
+  int vec_x, vec_y;  // float4 path legal
+  float p, inv_p;
+  int tiles_n;
+};
+
+template <int kMetric>
+__device__ __forceinline__ void ux_acc(float& acc, float a, float b, float p)
+{
+  if (kMetric == UX_L1) {
+    acc += fabsf(a - b);
+  } else if (kMetric == UX_L2 || kMetric == UX_L2SQRT) {
+    const float d = a - b;
+    acc           = fmaf(d, d, acc);
+  } else if (kMetric == UX_LINF) {
+    acc = fmaxf(acc, fabsf(a - b));
+  } else if (kMetric == UX_CANBERRA) {
+    const float d = fabsf(a - b);
+    const float s = fabsf(a) + fabsf(b);
+    // 0/0 -> 0 (scipy / reference convention); s == 0 implies d == 0
+    acc += (s == 0.f) ? 0.f : __fdividef(d, s);
+  } else {
+    const float d = fabsf(a - b);
+    acc += exp2f(p * __log2f(d));  // d == 0 -> log2 = -inf -> exp2 = 0
+  }
+}
+
+template <int kMetric>
+__device__ __forceinline__ float ux_fin(float acc, float inv_p)
+{
+  if (kMetric == UX_L2SQRT) return sqrtf(acc);
+  if (kMetric == UX_LP) return exp2f(inv_p * __log2f(acc));
+  return acc;
+}
+
+__device__ __forceinline__ float4 ux_load4(const float* base, int64_t rs, int64_t cs, int64_t row,
+                                           int64_t nrows, int kcol, int k, int vec)
+{
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < nrows) {
+    const float* p = base + row * rs;
+    if (vec && kcol + 3 < k) {
+      v = __ldg(reinterpret_cast<const float4*>(p + kcol));
+    } else {
+      if (kcol < k) v.x = __ldg(p + (int64_t)kcol * cs);
+      if (kcol + 1 < k) v.y = __ldg(p + (int64_t)(kcol + 1) * cs);
+      if (kcol + 2 < k) v.z = __ldg(p + (int64_t)(kcol + 2) * cs);
+      if (kcol + 3 < k) v.w = __ldg(p + (int64_t)(kcol + 3) * cs);
+    }
+  }
+  return v;
+}
+
+template <int kMetric>
+__global__ void __launch_bounds__(UX_THREADS, 1) unexpanded_simt_kernel(const UxParams p)
+{
+  extern __shared__ __align__(128) float ux_smem[];
+  float(*sx)[UX_BM * UX_KB] = reinterpret_cast<float(*)[UX_BM * UX_KB]>(ux_smem);
+  float(*sy)[UX_BN * UX_KB] = reinterpret_cast<float(*)[UX_BN * UX_KB]>(ux_smem + 2 * UX_BM * UX_KB);
+
+  const int tid = threadIdx.x;
+  const int tx  = tid & 15;  // column group
+  const int ty  = tid >> 4;  // row group
+  const int64_t tile = blockIdx.x;
+  const int64_t m0   = (tile / p.tiles_n) * UX_BM;
+  const int64_t n0   = (tile % p.tiles_n) * UX_BN;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nkb = (p.k + UX_KB - 1) / UX_KB;
+  float4 gx[4], gy[4];
+
+  auto gload = [&](int kb) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + UX_THREADS * i, row = f >> 3, c4 = f & 7;
+      gx[i] = ux_load4(p.x, p.xrs, p.xcs, m0 + row, p.m, kb * UX_KB + c4 * 4, p.k, p.vec_x);
+      gy[i] = ux_load4(p.y, p.yrs, p.ycs, n0 + row, p.n, kb * UX_KB + c4 * 4, p.k, p.vec_y);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + UX_THREADS * i, row = f >> 3, c4 = f & 7;
+      const int off = row * UX_KB + ((c4 ^ (row & 7)) << 2);
+      *reinterpret_cast<float4*>(&sx[buf][off]) = gx[i];
+      *reinterpret_cast<float4*>(&sy[buf][off]) = gy[i];
+    }
+  };
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nkb) gload(kb + 1);
+#pragma unroll 2
+    for (int c4 = 0; c4 < 8; ++c4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = ty + 16 * i;
+        a[i] = *reinterpret_cast<const float4*>(&sx[buf][row * UX_KB + ((c4 ^ (row & 7)) << 2)]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row  = tx + 16 * j;
+        const float4 b = *reinterpret_cast<const float4*>(&sy[buf][row * UX_KB + ((c4 ^ (row & 7)) << 2)]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ux_acc<kMetric>(acc[i][j], a[i].x, b.x, p.p);
+          ux_acc<kMetric>(acc[i][j], a[i].y, b.y, p.p);
+          ux_acc<kMetric>(acc[i][j], a[i].z, b.z, p.p);
+          ux_acc<kMetric>(acc[i][j], a[i].w, b.w, p.p);
+        }
+      }
+    }
+    if (kb + 1 < nkb) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gi = m0 + ty + 16 * i;
+    if (gi >= p.m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t gj = n0 + tx + 16 * j;
+      if (gj < p.n) __stcs(p.dist + gi * p.ldd + gj, ux_fin<kMetric>(acc[i][j], p.inv_p));
+    }
+  }
+}
+
+}  // namespace b2d
