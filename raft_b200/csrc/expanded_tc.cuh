@@ -17,8 +17,12 @@
 //                              registers, then either a swizzled smem transpose + full-line
 //                              coalesced streaming stores (pairwise) or a per-row running
 //                              min / arg-min + one packed 64-bit atomicMin per row per tile (NN).
-// Two 128x256 fp32 accumulators fill TMEM's 512 columns: MMA of tile t+1 overlaps the epilogue of
-// tile t.  Work item = (256-column block of y, run of 128-row tiles of x).  With k <= 128 the
+// A 128x256 output tile is computed as two 128x128 halves; each half owns two fp32 accumulators
+// in TMEM -- `main` (hi*hi) and `cross` (hi*lo + lo*hi) -- so the four 128-column slots fill TMEM's
+// 512 columns and the MMA of one half overlaps the epilogue of the other.  Keeping the small
+// cross terms out of the big accumulator matters: the tensor core truncates (round-toward-zero)
+// once per MMA at the accumulator's magnitude, so the bias grows with the number of MMAs that
+// touch `main`; this layout leaves 2 per k-block instead of 6 (measured: DESIGN.md, accuracy).  Work item = (256-column block of y, run of 128-row tiles of x).  With k <= 128 the
 // y block (both halves, all of K: <= 128 KB) stays resident in shared memory for the whole run and
 // only x tiles stream through a 4-stage ring, which cuts L2->SM operand traffic to ~21 B/clk/SM;
 // for larger k both operands stream per k-block.
@@ -148,39 +152,66 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(TC_BM, TC_BN);
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(TC_BM, TC_BN / 2);
       uint32_t a_it = 0, t_it = 0, it_local = 0;
+      // six K=16 steps of one k-block into one half: cross terms -> d+128, hi*hi -> d
+      auto mma_kblock = [&](uint32_t d_half, uint32_t a_addr, uint32_t b_addr, uint32_t acc) {
+        const uint64_t da = ptx::umma_desc_sw128(a_addr);
+        const uint64_t db = ptx::umma_desc_sw128(b_addr);
+        // descriptor start-address units are 16 B; inside the 128-B swizzled row:
+        //   hi k[0,16) +0, hi k[16,32) +2, lo k[0,16) +4, lo k[16,32) +6
+        ptx::mma_f16_ss(d_half + 128, da + 4, db + 0, idesc, acc);  // lo0 * hi0
+        ptx::mma_f16_ss(d_half + 128, da + 6, db + 2, idesc, 1u);   // lo1 * hi1
+        ptx::mma_f16_ss(d_half + 128, da + 0, db + 4, idesc, 1u);   // hi0 * lo0
+        ptx::mma_f16_ss(d_half + 128, da + 2, db + 6, idesc, 1u);   // hi1 * lo1
+        ptx::mma_f16_ss(d_half, da + 0, db + 0, idesc, acc);        // hi0 * hi0
+        ptx::mma_f16_ss(d_half, da + 2, db + 2, idesc, 1u);         // hi1 * hi1
+      };
       for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
         const int ch  = static_cast<int>(item / p.tiles_n);
         const int mt0 = ch * p.chunk;
         const int mt1 = min(mt0 + p.chunk, p.tiles_m);
         for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
-          const uint32_t as = t_it & 1, aph = (t_it >> 1) & 1;
-          ptx::mbar_wait(&tempty[as], aph ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t d_addr = tmem_base + as * TC_BN;
-          for (int kb = 0; kb < nkb; ++kb, ++a_it) {
-            if (kResident && mt == mt0) ptx::mbar_wait(&bfull[kb], it_local & 1);
-            const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
-            ptx::mbar_wait(&afull[s], ph);
+          const uint32_t tph = t_it & 1;
+          if (kResident) {
+            // A tile (nkb <= TC_STAGES stages) is consumed twice: half 0, then half 1
+            for (int h = 0; h < 2; ++h) {
+              ptx::mbar_wait(&tempty[h], tph ^ 1);
+              ptx::tc_fence_after();
+              const uint32_t d_half = tmem_base + h * 256;
+              for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t it = a_it + kb, s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                if (h == 0) {
+                  if (mt == mt0) ptx::mbar_wait(&bfull[kb], it_local & 1);
+                  ptx::mbar_wait(&afull[s], ph);
+                  ptx::tc_fence_after();
+                }
+                mma_kblock(d_half, ptx::smem_u32(a_base + s * TC_A_BYTES),
+                           ptx::smem_u32(b_base + kb * TC_B_BYTES + h * (TC_B_BYTES / 2)), kb > 0 ? 1u : 0u);
+                if (h == 1) {
+                  ptx::mma_commit(&aempty[s]);
+                  if (mt == mt1 - 1) ptx::mma_commit(&bempty[kb]);
+                }
+              }
+              ptx::mma_commit(&tfull[h]);
+            }
+            a_it += nkb;
+          } else {
+            ptx::mbar_wait(&tempty[0], tph ^ 1);
+            ptx::mbar_wait(&tempty[1], tph ^ 1);
             ptx::tc_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(a_base + s * TC_A_BYTES);
-            const uint32_t b_addr = ptx::smem_u32(b_base + (kResident ? kb : (int)s) * TC_B_BYTES);
-            const uint64_t da = ptx::umma_desc_sw128(a_addr);
-            const uint64_t db = ptx::umma_desc_sw128(b_addr);
-            // byte offsets inside the 128-B swizzled row (>>4 in descriptor units):
-            //   hi k[0,16) +0, hi k[16,32) +32, lo k[0,16) +64, lo k[16,32) +96
-            // lo*hi and hi*lo first (small terms), hi*hi last.
-            ptx::mma_f16_ss(d_addr, da + 4, db + 0, idesc, kb > 0 ? 1u : 0u);  // lo0 * hi0
-            ptx::mma_f16_ss(d_addr, da + 6, db + 2, idesc, 1u);                // lo1 * hi1
-            ptx::mma_f16_ss(d_addr, da + 0, db + 4, idesc, 1u);                // hi0 * lo0
-            ptx::mma_f16_ss(d_addr, da + 2, db + 6, idesc, 1u);                // hi1 * lo1
-            ptx::mma_f16_ss(d_addr, da + 0, db + 0, idesc, 1u);                // hi0 * hi0
-            ptx::mma_f16_ss(d_addr, da + 2, db + 2, idesc, 1u);                // hi1 * hi1
-            ptx::mma_commit(&aempty[s]);
-            if (kResident && mt == mt1 - 1) ptx::mma_commit(&bempty[kb]);
+            for (int kb = 0; kb < nkb; ++kb, ++a_it) {
+              const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
+              ptx::mbar_wait(&afull[s], ph);
+              ptx::tc_fence_after();
+              for (int h = 0; h < 2; ++h)
+                mma_kblock(tmem_base + h * 256, ptx::smem_u32(a_base + s * TC_A_BYTES),
+                           ptx::smem_u32(b_base + s * TC_B_BYTES + h * (TC_B_BYTES / 2)), kb > 0 ? 1u : 0u);
+              ptx::mma_commit(&aempty[s]);
+            }
+            ptx::mma_commit(&tfull[0]);
+            ptx::mma_commit(&tfull[1]);
           }
-          ptx::mma_commit(&tfull[as]);
         }
       }
     }
@@ -210,27 +241,36 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       ptx::bar_sync(1, 128);
 
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
-        const uint32_t as = t_it & 1, aph = (t_it >> 1) & 1;
-        const int64_t gi  = static_cast<int64_t>(mt) * TC_BM + row_in_t;
-        float2 rv         = make_float2(0.f, 0.f);
+        const uint32_t tph = t_it & 1;
+        const int64_t gi   = static_cast<int64_t>(mt) * TC_BM + row_in_t;
+        float2 rv          = make_float2(0.f, 0.f);
         if (gi < p.m) rv = __ldg(&p.xvec[gi]);
-        ptx::mbar_wait(&tfull[as], aph);
-        ptx::tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * TC_BN;
 
         float best_v = __int_as_float(0x7f800000);
         int best_j   = 0x7fffffff;
 
 #pragma unroll 1
         for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+          const int h = chunk >> 2;  // half of the tile this 32-column chunk belongs to
+          if ((chunk & 3) == 0) {
+            ptx::mbar_wait(&tfull[h], tph);
+            ptx::tc_fence_after();
+          }
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256 + (chunk & 3) * 32;
           uint32_t r[32];
-          ptx::tmem_ld_32x32(t_addr + chunk * 32, r);
-          ptx::tmem_ld_wait();
-          if (chunk == TC_BN / 32 - 1) {
-            // accumulator fully drained into registers: hand it back to the MMA warp
+          {
+            uint32_t rc[32];
+            ptx::tmem_ld_32x32(t_addr, r);
+            ptx::tmem_ld_32x32(t_addr + 128, rc);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(rc[c]));
+          }
+          if ((chunk & 3) == 3) {
+            // this half's accumulators are fully drained into registers: hand them back
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+            if (lane == 0) ptx::mbar_arrive(&tempty[h]);
           }
           const int cbase = chunk * 32;
           if (kEpi == EPI_STORE) {

@@ -28,7 +28,10 @@ def err_stats(got, ref, eps=1e-4):
     with np.errstate(divide="ignore", invalid="ignore"):
         rel = np.where(diff > eps, diff / den, diff)
     bad = (~oracle.compare_approx(got, ref, eps)).sum()
-    return f"max_rel={np.nanmax(rel):.3e} mean_rel={np.nanmean(rel):.3e} max_abs={np.nanmax(diff):.3e} bad={bad}/{got.size}"
+    with np.errstate(divide="ignore", invalid="ignore"):
+        true_rel = np.where(den > 0, diff / den, 0.0)
+    return (f"cmp_max={np.nanmax(rel):.3e} true_rel_max={np.nanmax(true_rel):.3e} "
+            f"true_rel_p99.9={np.nanquantile(true_rel, 0.999):.3e} max_abs={np.nanmax(diff):.3e} bad={bad}/{got.size}")
 
 
 def run_pw(metric, m, n, k, kind="blobs", p=2.0):
