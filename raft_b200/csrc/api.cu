@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -64,6 +65,22 @@ static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, in
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return B2D_OK;
+}
+
+// dist [m][n] fp32 (row pitch ldd), box = 32 x 32, SWIZZLE_128B (inner box = 128 bytes)
+static int make_dist_map(CUtensorMap* map, const float* base, int64_t m, int64_t n, int64_t ldd)
+{
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2]    = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldd) * 4};
+  cuuint32_t box[2]     = {32, 32};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(dist) failed: " + std::to_string((int)r));
   return B2D_OK;
 }
 
@@ -135,27 +152,33 @@ static int launch_prep(cudaStream_t s, const void* src, int64_t rs, int64_t cs, 
   return B2D_OK;
 }
 
-template <bool kRes, int kEpi>
-static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid)
+template <bool kRes, int kEpi, int kPost, bool kTma>
+static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                          const TcParams& p, int grid)
 {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  const size_t smem = tc_smem_bytes(kRes);
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem));
-  });
-  // the attribute is per device; set it again cheaply when several devices are in use
-  if (attr_err == cudaSuccess)
-    attr_err = cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem));
-  B2D_CUDA(attr_err);
-  expanded_tc_kernel<kRes, kEpi><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+  // the attribute is per device and per function: cheap, set on every launch
+  B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost, kTma>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES)));
+  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
 
-static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi)
+template <bool kRes>
+static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                           const TcParams& p, int grid, int post, bool tma)
+{
+  if (tma) {
+    if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, true>(s, ma, mb, md, p, grid);
+    if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, true>(s, ma, mb, md, p, grid);
+    return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, true>(s, ma, mb, md, p, grid);
+  }
+  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, false>(s, ma, mb, md, p, grid);
+  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, false>(s, ma, mb, md, p, grid);
+  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, false>(s, ma, mb, md, p, grid);
+}
+
+static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post)
 {
   int sms = 0, cc = 0;
   int rc  = device_sms(&sms, &cc);
@@ -175,19 +198,26 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.xvec     = w.xvec;
   p.yvec     = w.yvec;
   if (p.n_items == 0) return B2D_OK;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, md;
+  memset(&md, 0, sizeof(md));
   rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
   if (rc) return rc;
   rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN);
   if (rc) return rc;
   const int grid      = static_cast<int>(p.n_items < sms ? p.n_items : sms);
   const bool resident = p.nkb <= TC_MAX_RES_KB;
-  if (resident) {
-    return epi == EPI_STORE ? launch_tc_inst<true, EPI_STORE>(s, ma, mb, p, grid)
-                            : launch_tc_inst<true, EPI_MINLOC>(s, ma, mb, p, grid);
+  if (epi == EPI_MINLOC) {
+    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
+                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
-  return epi == EPI_STORE ? launch_tc_inst<false, EPI_STORE>(s, ma, mb, p, grid)
-                          : launch_tc_inst<false, EPI_MINLOC>(s, ma, mb, p, grid);
+  // TMA tensor store needs a 16-byte aligned base and row pitch
+  const bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0);
+  if (tma) {
+    rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
+    if (rc) return rc;
+  }
+  return resident ? launch_tc_store<true>(s, ma, mb, md, p, grid, post, tma)
+                  : launch_tc_store<false>(s, ma, mb, md, p, grid, post, tma);
 }
 
 template <int kMetric>
@@ -298,10 +328,10 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     if (rc) return rc;
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd; p.post = post;
+    p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd;
     p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy) ? 1 : 0;
     p.vec_ok    = (reinterpret_cast<uintptr_t>(dist) % 16 == 0 && ldd % 4 == 0) ? 1 : 0;
-    return launch_tc(s, w, p, k, EPI_STORE);
+    return launch_tc(s, w, p, k, EPI_STORE, post);
   }
 
   if (dtype != B2D_F32) return fail(B2D_ERR_UNSUPPORTED, "unexpanded metrics take fp32 inputs");
@@ -361,7 +391,7 @@ int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
-  return launch_tc(s, w, p, k, EPI_MINLOC);
+  return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 }
 
 int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys, int64_t m, int do_sqrt,

@@ -10,22 +10,28 @@
 // fp32), i.e. ~22 significant bits per operand -- fp32-grade, same idea as the reference's 3xTF32
 // but at the 2x higher kind::f16 rate and with 4 B/element staged instead of 8.
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0   TMA producer      cp.async.bulk.tensor 2-D, SWIZZLE_128B, mbarrier complete_tx
-//   warp 1   MMA issuer        one thread issues tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16
-//   warps 2-5 epilogue         tcgen05.ld 32x32b (thread == output row), fused epilogue in
-//                              registers, then either a swizzled smem transpose + full-line
-//                              coalesced streaming stores (pairwise) or a per-row running
-//                              min / arg-min + one packed 64-bit atomicMin per row per tile (NN).
+// Structure (one persistent CTA per SM, 320 threads):
+//   warp 0     TMA producer    cp.async.bulk.tensor 2-D, SWIZZLE_128B, mbarrier complete_tx
+//   warp 1     MMA issuer      one thread issues tcgen05.mma.cta_group::1.kind::f16, M128 N128 K16
+//   warps 2-5  epilogue of the left  128 columns of every tile  (one warp per TMEM lane quarter)
+//   warps 6-9  epilogue of the right 128 columns
 // A 128x256 output tile is computed as two 128x128 halves; each half owns two fp32 accumulators
 // in TMEM -- `main` (hi*hi) and `cross` (hi*lo + lo*hi) -- so the four 128-column slots fill TMEM's
 // 512 columns and the MMA of one half overlaps the epilogue of the other.  Keeping the small
-// cross terms out of the big accumulator matters: the tensor core truncates (round-toward-zero)
-// once per MMA at the accumulator's magnitude, so the bias grows with the number of MMAs that
-// touch `main`; this layout leaves 2 per k-block instead of 6 (measured: DESIGN.md, accuracy).  Work item = (256-column block of y, run of 128-row tiles of x).  With k <= 128 the
-// y block (both halves, all of K: <= 128 KB) stays resident in shared memory for the whole run and
-// only x tiles stream through a 4-stage ring, which cuts L2->SM operand traffic to ~21 B/clk/SM;
-// for larger k both operands stream per k-block.
+// cross terms out of the big accumulator matters: the tensor core aligns every product to the
+// accumulator's exponent and truncates, so the error grows with the number of MMAs that touch a
+// large accumulator; this layout leaves 2 per k-block instead of 6 (accuracy).
+// Epilogue (thread == output row, tcgen05.ld 32x32b): d = (main+cross) * (a.x*b.x) + (a.y+b.y) on
+// packed f32x2 pipes, then
+//   EPI_STORE   clamp / sqrt, swizzled st.shared, one TMA tensor store (32x32 box) per warp per
+//               32 columns -- whole 128-byte lines, clipped at the matrix edge by the hardware;
+//               manual coalesced stores when dist is not 16-byte aligned
+//   EPI_MINLOC  per-row running min / arg-min; one packed 64-bit atomicMin per row per half tile,
+//               skipped when the row's current global key is already smaller.
+// Work item = (256-column block of y, run of 128-row tiles of x).  With k <= 128 the y block
+// (both halves, all of K: <= 128 KB) stays resident in shared memory for the whole run and only
+// x tiles stream through a 4-stage ring, which cuts L2->SM operand traffic to ~21 B/clk/SM; for
+// larger k both operands stream per k-block.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -40,8 +46,9 @@ constexpr int TC_A_BYTES     = TC_BM * 128;  // one k-block of A: 128 rows x 128
 constexpr int TC_B_BYTES     = TC_BN * 128;  // one k-block of B: 256 rows x 128 B
 constexpr int TC_STAGES      = 4;
 constexpr int TC_MAX_RES_KB  = 4;            // resident-B variant: k <= 128
-constexpr int TC_THREADS     = 192;
-constexpr int TC_STG_FLOATS  = 32 * 32;      // per epilogue warp transpose buffer
+constexpr int TC_EPI_WARPS   = 8;
+constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_STG_FLOATS  = 32 * 32;      // per epilogue warp transpose buffer (4 KB)
 
 enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1 };
 enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
@@ -58,20 +65,16 @@ struct TcParams {
   // EPI_STORE
   float* dist;
   int64_t ldd;
-  int post;
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
-  int vec_ok;             // 16-byte aligned rows -> st.v4
+  int vec_ok;             // manual path: 16-byte aligned rows -> st.v4
   // EPI_MINLOC
   long long* keys;        // [m] packed (ordered float bits << 32 | index)
   int64_t idx_offset;
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(bool resident)
-{
-  size_t op = resident ? (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES * TC_A_BYTES
-                       : (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES);
-  return 1024 /*align slack*/ + op + 4 * TC_STG_FLOATS * 4 + TC_BN * 8 + 256;
-}
+constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES * TC_A_BYTES;  // 192 KB
+static_assert(TC_SMEM_OPERANDS == (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES), "both variants use the same carve");
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + (size_t)TC_EPI_WARPS * TC_STG_FLOATS * 4 + 2 * TC_BN * 4 + 256;
 
 // float -> int whose signed order equals the float order
 __device__ __forceinline__ int ordered_bits(float v)
@@ -80,25 +83,68 @@ __device__ __forceinline__ int ordered_bits(float v)
   return b < 0 ? (b ^ 0x7FFFFFFF) : b;
 }
 
-template <bool kResident, int kEpi>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                   const __grid_constant__ CUtensorMap tmap_b, const TcParams p)
+// packed f32x2 helpers (FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot)
+__device__ __forceinline__ uint64_t pk(float lo, float hi)
 {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  // carve
-  uint8_t* b_base = smem;                                                     // resident slabs or per-stage B
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk(uint32_t lo, uint32_t hi)
+{
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk(uint64_t v, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c)
+{
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+template <bool kResident, int kEpi, int kPost, bool kTma>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_d, const TcParams p)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // SWIZZLE_128B atoms need 1024-byte alignment; the dynamic window starts 1024-aligned (no static
+  // shared memory in this kernel).  Checked, not assumed: a misaligned base traps.
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* b_base = smem;  // resident slabs, or per-stage B
   uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES * TC_B_BYTES);
-  float* stg      = reinterpret_cast<float*>(a_base + TC_STAGES * TC_A_BYTES);
-  float2* colvec  = reinterpret_cast<float2*>(stg + 4 * TC_STG_FLOATS);
-  uint64_t* bars  = reinterpret_cast<uint64_t*>(colvec + TC_BN);
+  float* stg      = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);
+  float* col_cb   = stg + TC_EPI_WARPS * TC_STG_FLOATS;  // [256] b.x
+  float* col_tb   = col_cb + TC_BN;                      // [256] b.y
+  uint64_t* bars  = reinterpret_cast<uint64_t*>(col_tb + TC_BN);
   uint64_t* afull = bars;                  // [TC_STAGES]
   uint64_t* aempty = bars + TC_STAGES;     // [TC_STAGES]
   uint64_t* bfull = bars + 2 * TC_STAGES;  // [TC_MAX_RES_KB]
   uint64_t* bempty = bfull + TC_MAX_RES_KB;
-  uint64_t* tfull = bempty + TC_MAX_RES_KB;  // [2]
+  uint64_t* tfull = bempty + TC_MAX_RES_KB;  // [2]  one per half
   uint64_t* tempty = tfull + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -112,6 +158,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (kEpi == EPI_STORE && kTma) ptx::prefetch_tmap(&tmap_d);
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
@@ -218,122 +265,150 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     __syncwarp();
   } else {
     // ================================ epilogue warps ===============================
-    const int q        = warp & 3;            // TMEM lane quarter this warp may read
-    const int ew       = warp - 2;            // 0..3, staging buffer id
-    const int et       = threadIdx.x - 64;    // 0..127
+    const int q        = warp & 3;          // TMEM lane quarter this warp may read
+    const int ew       = warp - 2;          // 0..7
+    const int h        = ew >> 2;           // which 128-column half of every tile this warp drains
+    const int et       = threadIdx.x - 64;  // 0..255
     const int row_in_t = q * 32 + lane;
     float* my_stg      = stg + ew * TC_STG_FLOATS;
+    const uint64_t pol_st = ptx::policy_evict_first();
     uint32_t t_it      = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n_blk = static_cast<int>(item % p.tiles_n);
       const int ch    = static_cast<int>(item / p.tiles_n);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
-      // column pairs of this y block (shared by every tile of the item)
-      ptx::bar_sync(1, 128);
-      for (int c = et; c < TC_BN; c += 128) {
-        const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + c;
-        float2 cv;
+      // per-column epilogue pairs of this y block (shared by every tile of the item)
+      ptx::bar_sync(1, 32 * TC_EPI_WARPS);
+      {
+        const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
+        float2 cv        = make_float2(0.f, kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f);
         if (gj < p.n) cv = __ldg(&p.yvec[gj]);
-        else cv = make_float2(0.f, kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f);
-        colvec[c] = cv;
+        col_cb[et] = cv.x;
+        col_tb[et] = cv.y;
       }
-      ptx::bar_sync(1, 128);
+      ptx::bar_sync(1, 32 * TC_EPI_WARPS);
 
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
         const uint32_t tph = t_it & 1;
         const int64_t gi   = static_cast<int64_t>(mt) * TC_BM + row_in_t;
         float2 rv          = make_float2(0.f, 0.f);
-        if (gi < p.m) rv = __ldg(&p.xvec[gi]);
-
+        long long cur_key  = 0x7FFFFFFFFFFFFFFFll;
+        if (gi < p.m) {
+          rv = __ldg(&p.xvec[gi]);
+          if (kEpi == EPI_MINLOC) cur_key = *reinterpret_cast<volatile long long*>(&p.keys[gi]);
+        }
+        const uint64_t ra2 = pk(rv.x, rv.x), ta2 = pk(rv.y, rv.y);
         float best_v = __int_as_float(0x7f800000);
         int best_j   = 0x7fffffff;
 
+        ptx::mbar_wait(&tfull[h], tph);
+        ptx::tc_fence_after();
+
 #pragma unroll 1
-        for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
-          const int h = chunk >> 2;  // half of the tile this 32-column chunk belongs to
-          if ((chunk & 3) == 0) {
-            ptx::mbar_wait(&tfull[h], tph);
-            ptx::tc_fence_after();
-          }
-          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256 + (chunk & 3) * 32;
-          uint32_t r[32];
-          {
-            uint32_t rc[32];
-            ptx::tmem_ld_32x32(t_addr, r);
-            ptx::tmem_ld_32x32(t_addr + 128, rc);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(rc[c]));
-          }
-          if ((chunk & 3) == 3) {
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int cbase       = h * 128 + chunk * 32;  // first column of this chunk inside the tile
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256 + chunk * 32;
+          uint32_t r[32], rc[32];
+          ptx::tmem_ld_32x32(t_addr, r);
+          ptx::tmem_ld_32x32(t_addr + 128, rc);
+          ptx::tmem_ld_wait();
+          if (chunk == 3) {
             // this half's accumulators are fully drained into registers: hand them back
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[h]);
           }
-          const int cbase = chunk * 32;
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 cb = *reinterpret_cast<const float4*>(&col_cb[cbase + c]);
+            const float4 tb = *reinterpret_cast<const float4*>(&col_tb[cbase + c]);
+            const uint64_t s0 = add2(pk(r[c], r[c + 1]), pk(rc[c], rc[c + 1]));
+            const uint64_t s1 = add2(pk(r[c + 2], r[c + 3]), pk(rc[c + 2], rc[c + 3]));
+            const uint64_t m0 = mul2(ra2, pk(cb.x, cb.y));
+            const uint64_t m1 = mul2(ra2, pk(cb.z, cb.w));
+            uint64_t t0, t1;
+            if (kEpi == EPI_STORE) {
+              t0 = add2(ta2, pk(tb.x, tb.y));
+              t1 = add2(ta2, pk(tb.z, tb.w));
+            } else {  // the row-constant |x_i|^2 does not change the arg-min: added once at the end
+              t0 = pk(tb.x, tb.y);
+              t1 = pk(tb.z, tb.w);
+            }
+            unpk(fma2(s0, m0, t0), v[c], v[c + 1]);
+            unpk(fma2(s1, m1, t1), v[c + 2], v[c + 3]);
+          }
           if (kEpi == EPI_STORE) {
             const int64_t gj0 = static_cast<int64_t>(n_blk) * TC_BN + cbase;
+            if (kPost != POST_NONE) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float4 cv = *reinterpret_cast<const float4*>(&colvec[cbase + c]);
-              float v0 = fmaf(__uint_as_float(r[c]) * rv.x, cv.x, rv.y + cv.y);
-              float v1 = fmaf(__uint_as_float(r[c + 1]) * rv.x, cv.z, rv.y + cv.w);
-              if (p.post != POST_NONE) {
-                v0 = fmaxf(v0, 0.f);
-                v1 = fmaxf(v1, 0.f);
-                if (p.diag_zero) {
-                  if (gi == gj0 + c) v0 = 0.f;
-                  if (gi == gj0 + c + 1) v1 = 0.f;
-                }
-                if (p.post == POST_CLAMP_SQRT) {
-                  asm("sqrt.approx.f32 %0, %1;" : "=f"(v0) : "f"(v0));
-                  asm("sqrt.approx.f32 %0, %1;" : "=f"(v1) : "f"(v1));
-                }
+              for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+              if (p.diag_zero && gi >= gj0 && gi < gj0 + 32) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (gi == gj0 + c) v[c] = 0.f;
               }
-              r[c]     = __float_as_uint(v0);
-              r[c + 1] = __float_as_uint(v1);
-            }
-            // transpose through shared memory (16-byte chunks XOR-swizzled by row: conflict-free
-            // both ways) so that every global store instruction writes whole 128-byte row segments
+              if (kPost == POST_CLAMP_SQRT) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              float4 v = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
-                                     __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
-              *reinterpret_cast<float4*>(my_stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = v;
-            }
-            __syncwarp();
-            const int c4 = lane & 7;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr      = it * 4 + (lane >> 3);
-              const float4 v    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-              const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
-              const int64_t gj  = gj0 + c4 * 4;
-              if (gi2 < p.m) {
-                float* dst = p.dist + gi2 * p.ldd + gj;
-                if (p.vec_ok && gj + 3 < p.n) {
-                  ptx::st_global_cs_v4(dst, v);
-                } else {
-                  if (gj < p.n) ptx::st_global_cs(dst, v.x);
-                  if (gj + 1 < p.n) ptx::st_global_cs(dst + 1, v.y);
-                  if (gj + 2 < p.n) ptx::st_global_cs(dst + 2, v.z);
-                  if (gj + 3 < p.n) ptx::st_global_cs(dst + 3, v.w);
-                }
+                for (int c = 0; c < 32; ++c) asm("sqrt.approx.f32 %0, %1;" : "=f"(v[c]) : "f"(v[c]));
               }
             }
-            __syncwarp();
+            // stage the 32x32 block in shared memory, 16-byte chunks XOR-swizzled by (row & 7):
+            // conflict-free, and exactly the SWIZZLE_128B pattern the TMA store descriptor expects
+            if (kTma) {
+              if (lane == 0) ptx::tma_store_wait_read();  // previous chunk's store has left smem
+              __syncwarp();
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              *reinterpret_cast<float4*>(my_stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+                make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            if (kTma) {
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_2d(&tmap_d, my_stg, static_cast<int32_t>(gj0), mt * TC_BM + q * 32, pol_st);
+                ptx::tma_store_commit();
+              }
+            } else {
+              __syncwarp();
+              const int c4 = lane & 7;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr      = it * 4 + (lane >> 3);
+                const float4 o    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
+                const int64_t gj  = gj0 + c4 * 4;
+                if (gi2 < p.m) {
+                  float* dst = p.dist + gi2 * p.ldd + gj;
+                  if (p.vec_ok && gj + 3 < p.n) {
+                    ptx::st_global_cs_v4(dst, o);
+                  } else {
+                    if (gj < p.n) ptx::st_global_cs(dst, o.x);
+                    if (gj + 1 < p.n) ptx::st_global_cs(dst + 1, o.y);
+                    if (gj + 2 < p.n) ptx::st_global_cs(dst + 2, o.z);
+                    if (gj + 3 < p.n) ptx::st_global_cs(dst + 3, o.w);
+                  }
+                }
+              }
+              __syncwarp();
+            }
           } else {
-            // running (min, argmin) over ascending column index; strict '<' keeps the smallest
-            // index on ties (raft::argmin_op, cpp/include/raft/core/operators.hpp:187-194)
+            // min over the chunk with 3-input FMNMX, then (rarely) locate it: ascending scan with
+            // '==' keeps the smallest column on ties, strict '<' against the running best keeps the
+            // earliest chunk (raft::argmin_op, cpp/include/raft/core/operators.hpp:187-194)
+            float mn = min3(v[0], v[1], v[2]);
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float4 cv = *reinterpret_cast<const float4*>(&colvec[cbase + c]);
-              const float v0  = fmaf(__uint_as_float(r[c]) * rv.x, cv.x, cv.y);
-              const float v1  = fmaf(__uint_as_float(r[c + 1]) * rv.x, cv.z, cv.w);
-              if (v0 < best_v) { best_v = v0; best_j = cbase + c; }
-              if (v1 < best_v) { best_v = v1; best_j = cbase + c + 1; }
+            for (int c = 3; c < 31; c += 2) mn = min3(mn, v[c], v[c + 1]);
+            mn = fminf(mn, v[31]);
+            if (mn < best_v) {
+              best_v = mn;
+              int j  = 31;
+#pragma unroll
+              for (int c = 30; c >= 0; --c)
+                if (v[c] == mn) j = c;
+              best_j = cbase + j;
             }
           }
         }
@@ -341,10 +416,14 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (gi < p.m && best_j != 0x7fffffff) {
             const long long gj  = static_cast<long long>(n_blk) * TC_BN + best_j + p.idx_offset;
             const long long key = (static_cast<long long>(ordered_bits(best_v)) << 32) | (gj & 0xFFFFFFFFll);
-            atomicMin(&p.keys[gi], key);
+            if (key < cur_key) atomicMin(&p.keys[gi], key);
           }
         }
       }
+    }
+    if (kEpi == EPI_STORE && kTma) {
+      if (lane == 0) ptx::tma_store_wait_all();
+      __syncwarp();
     }
   }
 

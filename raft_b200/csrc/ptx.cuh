@@ -97,6 +97,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       "r"(c1), "l"(policy)
     : "memory");
 }
+// 2-D tiled store shared -> global (bulk async-group completion); OOB parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1,
+                                             uint64_t policy)
+{
+  asm volatile(
+    "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+    :
+    : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+    : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t policy_evict_last()
 {
   uint64_t p;
