@@ -211,7 +211,9 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
                     : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
   // TMA tensor store needs a 16-byte aligned base and row pitch
-  const bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0);
+  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0);
+  if (getenv("B2D_NO_TMA_STORE")) tma = false;  // experiment knob
+  { const char* e = getenv("B2D_ST_POLICY"); p.st_policy = e ? atoi(e) : 0; }
   if (tma) {
     rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
     if (rc) return rc;

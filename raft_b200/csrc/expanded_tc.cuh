@@ -67,6 +67,7 @@ struct TcParams {
   int64_t ldd;
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
   int vec_ok;             // manual path: 16-byte aligned rows -> st.v4
+  int st_policy;          // experiment knob: L2 policy of the tensor store (0 first, 1 normal, 2 last)
   // EPI_MINLOC
   long long* keys;        // [m] packed (ordered float bits << 32 | index)
   int64_t idx_offset;
@@ -170,69 +171,75 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     // ================================ TMA producer =================================
-    if (lane == 0) {
-      const uint64_t pol = ptx::policy_evict_last();
-      uint32_t a_it = 0, it_local = 0;
-      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-        const int n_blk = static_cast<int>(item % p.tiles_n);
-        const int ch    = static_cast<int>(item / p.tiles_n);
-        const int mt0   = ch * p.chunk;
-        const int mt1   = min(mt0 + p.chunk, p.tiles_m);
-        for (int mt = mt0; mt < mt1; ++mt) {
-          for (int kb = 0; kb < nkb; ++kb, ++a_it) {
-            if (kResident && mt == mt0) {
-              ptx::mbar_wait(&bempty[kb], (it_local & 1) ^ 1);
+    // The whole warp runs the loop with warp-uniform values and one elected lane issues: inside a
+    // divergent `if (lane == 0)` the compiler cannot keep descriptors / barrier addresses in
+    // uniform registers and wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST waterfall
+    // loop (measured: the MMA issue loop itself became the bottleneck).
+    const uint64_t pol = ptx::policy_evict_last();
+    uint32_t a_it = 0, it_local = 0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+      const int n_blk = static_cast<int>(item % p.tiles_n);
+      const int ch    = static_cast<int>(item / p.tiles_n);
+      const int mt0   = ch * p.chunk;
+      const int mt1   = min(mt0 + p.chunk, p.tiles_m);
+      for (int mt = mt0; mt < mt1; ++mt) {
+        for (int kb = 0; kb < nkb; ++kb, ++a_it) {
+          if (kResident && mt == mt0) {
+            ptx::mbar_wait(&bempty[kb], (it_local & 1) ^ 1);
+            if (ptx::elect_one()) {
               ptx::mbar_expect_tx(&bfull[kb], TC_B_BYTES);
               ptx::tma_load_2d(b_base + kb * TC_B_BYTES, &tmap_b, &bfull[kb], kb * 64, n_blk * TC_BN, pol);
             }
-            const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
-            ptx::mbar_wait(&aempty[s], ph ^ 1);
+          }
+          const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
+          ptx::mbar_wait(&aempty[s], ph ^ 1);
+          if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&afull[s], kResident ? TC_A_BYTES : TC_A_BYTES + TC_B_BYTES);
             ptx::tma_load_2d(a_base + s * TC_A_BYTES, &tmap_a, &afull[s], kb * 64, mt * TC_BM, pol);
             if (!kResident)
               ptx::tma_load_2d(b_base + s * TC_B_BYTES, &tmap_b, &afull[s], kb * 64, n_blk * TC_BN, pol);
           }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(TC_BM, TC_BN / 2);
-      uint32_t a_it = 0, t_it = 0, it_local = 0;
-      // six K=16 steps of one k-block into one half: cross terms -> d+128, hi*hi -> d
-      auto mma_kblock = [&](uint32_t d_half, uint32_t a_addr, uint32_t b_addr, uint32_t acc) {
-        const uint64_t da = ptx::umma_desc_sw128(a_addr);
-        const uint64_t db = ptx::umma_desc_sw128(b_addr);
-        // descriptor start-address units are 16 B; inside the 128-B swizzled row:
-        //   hi k[0,16) +0, hi k[16,32) +2, lo k[0,16) +4, lo k[16,32) +6
-        ptx::mma_f16_ss(d_half + 128, da + 4, db + 0, idesc, acc);  // lo0 * hi0
-        ptx::mma_f16_ss(d_half + 128, da + 6, db + 2, idesc, 1u);   // lo1 * hi1
-        ptx::mma_f16_ss(d_half + 128, da + 0, db + 4, idesc, 1u);   // hi0 * lo0
-        ptx::mma_f16_ss(d_half + 128, da + 2, db + 6, idesc, 1u);   // hi1 * lo1
-        ptx::mma_f16_ss(d_half, da + 0, db + 0, idesc, acc);        // hi0 * hi0
-        ptx::mma_f16_ss(d_half, da + 2, db + 2, idesc, 1u);         // hi1 * hi1
-      };
-      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-        const int ch  = static_cast<int>(item / p.tiles_n);
-        const int mt0 = ch * p.chunk;
-        const int mt1 = min(mt0 + p.chunk, p.tiles_m);
-        for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
-          const uint32_t tph = t_it & 1;
-          if (kResident) {
-            // A tile (nkb <= TC_STAGES stages) is consumed twice: half 0, then half 1
-            for (int h = 0; h < 2; ++h) {
-              ptx::mbar_wait(&tempty[h], tph ^ 1);
-              ptx::tc_fence_after();
-              const uint32_t d_half = tmem_base + h * 256;
-              for (int kb = 0; kb < nkb; ++kb) {
-                const uint32_t it = a_it + kb, s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-                if (h == 0) {
-                  if (mt == mt0) ptx::mbar_wait(&bfull[kb], it_local & 1);
-                  ptx::mbar_wait(&afull[s], ph);
-                  ptx::tc_fence_after();
-                }
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(TC_BM, TC_BN / 2);
+    uint32_t a_it = 0, t_it = 0, it_local = 0;
+    // six K=16 steps of one k-block into one half: cross terms -> d+128, hi*hi -> d
+    auto mma_kblock = [&](uint32_t d_half, uint32_t a_addr, uint32_t b_addr, uint32_t acc) {
+      const uint64_t da = ptx::umma_desc_sw128(a_addr);
+      const uint64_t db = ptx::umma_desc_sw128(b_addr);
+      // descriptor start-address units are 16 B; inside the 128-B swizzled row:
+      //   hi k[0,16) +0, hi k[16,32) +2, lo k[0,16) +4, lo k[16,32) +6
+      ptx::mma_f16_ss(d_half + 128, da + 4, db + 0, idesc, acc);  // lo0 * hi0
+      ptx::mma_f16_ss(d_half + 128, da + 6, db + 2, idesc, 1u);   // lo1 * hi1
+      ptx::mma_f16_ss(d_half + 128, da + 0, db + 4, idesc, 1u);   // hi0 * lo0
+      ptx::mma_f16_ss(d_half + 128, da + 2, db + 6, idesc, 1u);   // hi1 * lo1
+      ptx::mma_f16_ss(d_half, da + 0, db + 0, idesc, acc);        // hi0 * hi0
+      ptx::mma_f16_ss(d_half, da + 2, db + 2, idesc, 1u);         // hi1 * hi1
+    };
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+      const int ch  = static_cast<int>(item / p.tiles_n);
+      const int mt0 = ch * p.chunk;
+      const int mt1 = min(mt0 + p.chunk, p.tiles_m);
+      for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
+        const uint32_t tph = t_it & 1;
+        if (kResident) {
+          // A tile (nkb <= TC_STAGES stages) is consumed twice: half 0, then half 1
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&tempty[h], tph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_half = tmem_base + h * 256;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t it = a_it + kb, s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+              if (h == 0) {
+                if (mt == mt0) ptx::mbar_wait(&bfull[kb], it_local & 1);
+                ptx::mbar_wait(&afull[s], ph);
+                ptx::tc_fence_after();
+              }
+              if (ptx::elect_one()) {
                 mma_kblock(d_half, ptx::smem_u32(a_base + s * TC_A_BYTES),
                            ptx::smem_u32(b_base + kb * TC_B_BYTES + h * (TC_B_BYTES / 2)), kb > 0 ? 1u : 0u);
                 if (h == 1) {
@@ -240,29 +247,36 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                   if (mt == mt1 - 1) ptx::mma_commit(&bempty[kb]);
                 }
               }
-              ptx::mma_commit(&tfull[h]);
+              __syncwarp();
             }
-            a_it += nkb;
-          } else {
-            ptx::mbar_wait(&tempty[0], tph ^ 1);
-            ptx::mbar_wait(&tempty[1], tph ^ 1);
+            if (ptx::elect_one()) ptx::mma_commit(&tfull[h]);
+            __syncwarp();
+          }
+          a_it += nkb;
+        } else {
+          ptx::mbar_wait(&tempty[0], tph ^ 1);
+          ptx::mbar_wait(&tempty[1], tph ^ 1);
+          ptx::tc_fence_after();
+          for (int kb = 0; kb < nkb; ++kb, ++a_it) {
+            const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
+            ptx::mbar_wait(&afull[s], ph);
             ptx::tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb, ++a_it) {
-              const uint32_t s = a_it % TC_STAGES, ph = (a_it / TC_STAGES) & 1;
-              ptx::mbar_wait(&afull[s], ph);
-              ptx::tc_fence_after();
+            if (ptx::elect_one()) {
               for (int h = 0; h < 2; ++h)
                 mma_kblock(tmem_base + h * 256, ptx::smem_u32(a_base + s * TC_A_BYTES),
                            ptx::smem_u32(b_base + s * TC_B_BYTES + h * (TC_B_BYTES / 2)), kb > 0 ? 1u : 0u);
               ptx::mma_commit(&aempty[s]);
             }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) {
             ptx::mma_commit(&tfull[0]);
             ptx::mma_commit(&tfull[1]);
           }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     // ================================ epilogue warps ===============================
     const int q        = warp & 3;          // TMEM lane quarter this warp may read
@@ -271,7 +285,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int et       = threadIdx.x - 64;  // 0..255
     const int row_in_t = q * 32 + lane;
     float* my_stg      = stg + ew * TC_STG_FLOATS;
-    const uint64_t pol_st = ptx::policy_evict_first();
+    const uint64_t pol_st = p.st_policy == 0 ? ptx::policy_evict_first()
+                            : (p.st_policy == 1 ? ptx::policy_evict_normal() : ptx::policy_evict_last());
     uint32_t t_it      = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n_blk = static_cast<int>(item % p.tiles_n);
@@ -305,13 +320,16 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::mbar_wait(&tfull[h], tph);
         ptx::tc_fence_after();
 
+        const uint32_t t_addr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256;
+        uint32_t r[32], rc[32];
+        ptx::tmem_ld_32x32(t_addr0, r);
+        ptx::tmem_ld_32x32(t_addr0 + 128, rc);
+        // fast store path: the whole 32x32 block of this warp is inside the matrix
+        const bool rows_in = static_cast<int64_t>(mt) * TC_BM + q * 32 + 31 < p.m;
+
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
-          const int cbase       = h * 128 + chunk * 32;  // first column of this chunk inside the tile
-          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256 + chunk * 32;
-          uint32_t r[32], rc[32];
-          ptx::tmem_ld_32x32(t_addr, r);
-          ptx::tmem_ld_32x32(t_addr + 128, rc);
+          const int cbase = h * 128 + chunk * 32;  // first column of this chunk inside the tile
           ptx::tmem_ld_wait();
           if (chunk == 3) {
             // this half's accumulators are fully drained into registers: hand them back
@@ -338,6 +356,10 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
             unpk(fma2(s0, m0, t0), v[c], v[c + 1]);
             unpk(fma2(s1, m1, t1), v[c + 2], v[c + 3]);
+          }
+          if (chunk < 3) {  // r / rc are dead: prefetch the next 32 columns while this chunk is stored
+            ptx::tmem_ld_32x32(t_addr0 + (chunk + 1) * 32, r);
+            ptx::tmem_ld_32x32(t_addr0 + (chunk + 1) * 32 + 128, rc);
           }
           if (kEpi == EPI_STORE) {
             const int64_t gj0 = static_cast<int64_t>(n_blk) * TC_BN + cbase;
@@ -374,21 +396,33 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             } else {
               __syncwarp();
               const int c4 = lane & 7;
+              if (rows_in && p.vec_ok && gj0 + 31 < p.n) {
+                float* dst = p.dist + (static_cast<int64_t>(mt) * TC_BM + q * 32 + (lane >> 3)) * p.ldd + gj0 + c4 * 4;
+                const int64_t step = 4 * p.ldd;
 #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int rr      = it * 4 + (lane >> 3);
-                const float4 o    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-                const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
-                const int64_t gj  = gj0 + c4 * 4;
-                if (gi2 < p.m) {
-                  float* dst = p.dist + gi2 * p.ldd + gj;
-                  if (p.vec_ok && gj + 3 < p.n) {
-                    ptx::st_global_cs_v4(dst, o);
-                  } else {
-                    if (gj < p.n) ptx::st_global_cs(dst, o.x);
-                    if (gj + 1 < p.n) ptx::st_global_cs(dst + 1, o.y);
-                    if (gj + 2 < p.n) ptx::st_global_cs(dst + 2, o.z);
-                    if (gj + 3 < p.n) ptx::st_global_cs(dst + 3, o.w);
+                for (int it = 0; it < 8; ++it) {
+                  const int rr   = it * 4 + (lane >> 3);
+                  const float4 o = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                  ptx::st_global_cs_v4(dst, o);
+                  dst += step;
+                }
+              } else {
+#pragma unroll 1
+                for (int it = 0; it < 8; ++it) {
+                  const int rr      = it * 4 + (lane >> 3);
+                  const float4 o    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                  const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
+                  const int64_t gj  = gj0 + c4 * 4;
+                  if (gi2 < p.m) {
+                    float* dst = p.dist + gi2 * p.ldd + gj;
+                    if (p.vec_ok && gj + 3 < p.n) {
+                      ptx::st_global_cs_v4(dst, o);
+                    } else {
+                      if (gj < p.n) ptx::st_global_cs(dst, o.x);
+                      if (gj + 1 < p.n) ptx::st_global_cs(dst + 1, o.y);
+                      if (gj + 2 < p.n) ptx::st_global_cs(dst + 2, o.z);
+                      if (gj + 3 < p.n) ptx::st_global_cs(dst + 3, o.w);
+                    }
                   }
                 }
               }
