@@ -1,0 +1,117 @@
+"""CPU tier: host-side mirror of the pylibraft conventions and the multi-GPU exchange logic
+(world_size-2 gloo run of the packed min-loc all-reduce)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from raft_b200.common.cai_wrapper import cai_wrapper
+from raft_b200.distance.distance_type import DISTANCE_TYPES, DistanceType, resolve_metric
+from raft_b200.distance.fused_l2_nn import shard_bounds
+from raft_b200.distance.pairwise_distance import _layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeCai:
+    def __init__(self, arr, ptr=0x1000):
+        self.__cuda_array_interface__ = {"shape": arr.shape, "typestr": arr.dtype.str, "version": 3,
+                                         "data": (ptr, False),
+                                         "strides": None if arr.flags.c_contiguous else arr.strides}
+
+
+def test_distance_type_values_match_reference_enum():
+    assert int(DistanceType.L2Expanded) == 0 and int(DistanceType.L2SqrtExpanded) == 1
+    assert int(DistanceType.CosineExpanded) == 2 and int(DistanceType.L1) == 3
+    assert int(DistanceType.LpUnexpanded) == 9 and int(DistanceType.CorrelationExpanded) == 10
+    assert int(DistanceType.Precomputed) == 100
+    assert {int(v) for v in DistanceType} == {int(v) for v in oracle.DistanceType}
+
+
+def test_metric_strings():
+    assert resolve_metric("euclidean") == DistanceType.L2SqrtExpanded
+    assert resolve_metric("sqeuclidean") == DistanceType.L2Expanded
+    assert resolve_metric("cityblock") == DistanceType.L1
+    assert resolve_metric("chebyshev") == DistanceType.Linf
+    assert resolve_metric("minkowski") == DistanceType.LpUnexpanded
+    assert resolve_metric("L2Unexpanded") == DistanceType.L2Unexpanded
+    assert resolve_metric(8) == DistanceType.Canberra
+    with pytest.raises(ValueError):
+        resolve_metric("jaccard")
+    assert set(DISTANCE_TYPES) >= {"l2", "l1", "cosine", "correlation", "canberra", "inner_product", "lp"}
+
+
+def test_cai_wrapper_and_layout():
+    a = np.zeros((5, 7), np.float32)
+    w = cai_wrapper(FakeCai(a))
+    assert w.shape == (5, 7) and w.c_contiguous and not w.f_contiguous and w.data == 0x1000
+    assert _layout(w) == (True, 7)
+    f = np.asfortranarray(a)
+    wf = cai_wrapper(FakeCai(f))
+    assert wf.f_contiguous and _layout(wf) == (False, 5)
+    padded = np.zeros((5, 16), np.float32)[:, :7]
+    assert _layout(cai_wrapper(FakeCai(padded))) == (True, 16)
+    with pytest.raises(TypeError):
+        cai_wrapper(FakeCai(a)).validate_shape_dtype(expected_dtype=np.float64)
+    with pytest.raises(ValueError):
+        cai_wrapper(FakeCai(a)).validate_shape_dtype(expected_dims=1)
+    with pytest.raises(TypeError):
+        cai_wrapper(a)
+
+
+def test_shard_bounds_cover_database_exactly():
+    for n, w in ((8_000_000, 8), (1001, 4), (7, 8), (5, 1)):
+        cuts = [shard_bounds(n, w, r) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    sys.path.insert(0, os.environ["B2D_ROOT"])
+    import numpy as np, torch, torch.distributed as dist
+    import oracle
+    from raft_b200.distance.fused_l2_nn import shard_bounds
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["B2D_PORT"],
+                            rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    x, _, c = oracle.make_blobs(257, 24, seed=11)
+    y, _, _ = oracle.make_blobs(1003, 24, seed=12, centers=c)
+    y[500] = y[3]                      # a tie across shards: the smaller global index must win
+    x[0] = y[3]
+    lo, hi = shard_bounds(y.shape[0], world, rank)
+    # what the GPU kernel leaves in `keys` for this shard (host model: oracle.pack_minloc)
+    d = oracle.pairwise_distance(x, y[lo:hi], oracle.DistanceType.L2Expanded)
+    xn = oracle.row_norm_sq(x)
+    loc = np.argmin(d, axis=1)
+    v = (d[np.arange(len(x)), loc] - xn).astype(np.float32)     # |y|^2 - 2xy, as the kernel packs it
+    keys = torch.from_numpy(oracle.pack_minloc(v, loc + lo))
+    dist.all_reduce(keys, op=dist.ReduceOp.MIN)                 # the ONE exchange step
+    val, idx = oracle.unpack_minloc(keys.numpy())
+    ref_idx, ref_val = oracle.fused_l2_nn(x, y)
+    assert (idx == ref_idx).all(), (rank, np.nonzero(idx != ref_idx))
+    assert idx[0] == 3
+    assert np.allclose(np.maximum(val.astype(np.float64) + xn, 0), ref_val, rtol=1e-4, atol=1e-3)
+    dist.barrier(); dist.destroy_process_group()
+    print("rank", rank, "ok")
+''')
+
+
+def test_minloc_allreduce_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29000 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", B2D_ROOT=ROOT, B2D_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert "ok" in out

@@ -1,0 +1,207 @@
+"""GPU tier: raft_b200.distance.pairwise_distance (through the C ABI) against the CPU oracle.
+
+Shapes follow the reference's historical distance tests ({1024,1024,32}, {1024,32,1024},
+{32,1024,1024}) plus ragged sizes, x==y aliasing, padded leading dimensions,
+Fortran order and caller-provided outputs.  Tolerance: 1e-4 relative with the absolute-below-eps
+rule of raft::CompareApprox (cpp/tests/test_utils.h:31-45), as BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import DistanceType as DT
+from raft_b200 import LogicError
+from raft_b200.common import DeviceResources, device_ndarray, set_output_as
+from raft_b200.distance import pairwise_distance
+
+pytestmark = pytest.mark.gpu
+EPS = 1e-4
+
+EXPANDED = [DT.L2Expanded, DT.L2SqrtExpanded, DT.CosineExpanded, DT.CorrelationExpanded]
+UNEXPANDED = [DT.L1, DT.L2Unexpanded, DT.L2SqrtUnexpanded, DT.Linf, DT.Canberra, DT.LpUnexpanded]
+
+
+def blobs(m, n, k, seed=0):
+    x, _, c = oracle.make_blobs(m, k, seed=1234 + seed)
+    y, _, _ = oracle.make_blobs(n, k, seed=4321 + seed, centers=c)
+    return x, y
+
+
+def run(x, y, metric, p=2.0, **kw):
+    out = pairwise_distance(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), metric=metric, p=p, **kw)
+    return out.copy_to_host()
+
+
+def check(got, ref, eps=EPS):
+    ok, msg = oracle.match_approx(got, ref, eps)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("metric", EXPANDED + UNEXPANDED)
+@pytest.mark.parametrize("shape", [(1024, 1024, 32), (333, 257, 45), (129, 300, 128), (64, 50, 7)])
+def test_metric_vs_oracle(metric, shape):
+    x, y = blobs(*shape)
+    check(run(x, y, metric, p=3.0), oracle.pairwise_distance(x, y, metric, 3.0))
+
+
+def test_inner_product_vs_oracle():
+    # inner products cancel to ~0 for some pairs: compare against the magnitude |x||y|
+    x, y = blobs(500, 400, 100)
+    got = run(x, y, DT.InnerProduct)
+    ref = oracle.pairwise_distance(x, y, DT.InnerProduct)
+    scale = np.sqrt(oracle.row_norm_sq(x))[:, None] * np.sqrt(oracle.row_norm_sq(y))[None, :]
+    assert np.abs(got - ref).max() <= 1e-5 * scale.max()
+    assert (np.abs(got - ref) <= 1e-5 * scale + 1e-6).all()
+
+
+@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.CosineExpanded, DT.L1])
+@pytest.mark.parametrize("shape", [(1024, 32, 1024), (32, 1024, 1024)])
+def test_reference_test_shapes_large_k(metric, shape):
+    # k = 1024: the tensor-core accumulator truncates per MMA, error grows with k;
+    # the reference's own tests used 1e-3 for these shapes
+    x, y = blobs(*shape)
+    check(run(x, y, metric), oracle.pairwise_distance(x, y, metric), eps=1e-3)
+
+
+@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.L2SqrtExpanded, DT.CosineExpanded, DT.L1, DT.Linf])
+def test_uniform_data(metric):
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, (700, 96)).astype(np.float32)
+    y = rng.uniform(-1, 1, (450, 96)).astype(np.float32)
+    check(run(x, y, metric), oracle.pairwise_distance(x, y, metric))
+
+
+def test_golden_fixtures(golden):
+    for case in ("small", "cfg1"):
+        x, y = golden[f"{case}_x"], golden[f"{case}_y"]
+        for name in ("L2Expanded", "L2SqrtExpanded", "CosineExpanded", "L1", "L2Unexpanded", "Linf",
+                     "Canberra", "CorrelationExpanded"):
+            check(run(x, y, DT[name]), golden[f"{case}_{name}"])
+        check(run(x, y, DT.LpUnexpanded, p=3.0), golden[f"{case}_LpUnexpanded_p3"])
+
+
+def test_config1_scipy_metric_strings():
+    """BASELINE.json configs[0]: 1024x1024x32 fp32 vs cdist (the oracle is pinned to cdist)."""
+    x, y = blobs(1024, 1024, 32)
+    for name, mt in (("euclidean", DT.L2SqrtExpanded), ("sqeuclidean", DT.L2Expanded), ("cityblock", DT.L1),
+                     ("chebyshev", DT.Linf), ("canberra", DT.Canberra), ("cosine", DT.CosineExpanded),
+                     ("correlation", DT.CorrelationExpanded)):
+        check(run(x, y, name), oracle.pairwise_distance(x, y, mt))
+    check(run(x, y, "minkowski", p=1.5), oracle.pairwise_distance(x, y, DT.LpUnexpanded, 1.5))
+
+
+def test_aliased_inputs_zero_diagonal():
+    x, _ = blobs(300, 1, 64)
+    xt = torch.from_numpy(x).cuda()
+    for metric in (DT.L2Expanded, DT.L2SqrtExpanded):
+        got = pairwise_distance(xt, xt, metric=metric).copy_to_host()
+        assert (np.diag(got) == 0).all()
+        check(got, oracle.pairwise_distance(x, x, metric))
+    got = pairwise_distance(xt, xt, metric=DT.L1).copy_to_host()
+    assert (np.diag(got) == 0).all()
+
+
+def test_symmetry_property():
+    x, y = blobs(260, 390, 96)
+    for metric in (DT.L2Expanded, DT.CosineExpanded, DT.L1):
+        a = run(x, y, metric)
+        b = run(y, x, metric)
+        assert np.array_equal(a, b.T) or oracle.match_approx(a, b.T, 1e-6)[0]
+
+
+def test_padded_leading_dimensions_and_out_param():
+    x, y = blobs(200, 150, 40)
+    xp = torch.zeros(200, 48, device="cuda"); xp[:, :40] = torch.from_numpy(x).cuda()
+    yp = torch.zeros(150, 56, device="cuda"); yp[:, :40] = torch.from_numpy(y).cuda()
+    outp = torch.full((200, 160), -7.0, device="cuda")
+    for metric in (DT.L2Expanded, DT.L1):
+        ret = pairwise_distance(xp[:, :40], yp[:, :40], out=outp[:, :150], metric=metric)
+        assert ret is not None
+        got = outp.cpu().numpy()
+        check(got[:, :150], oracle.pairwise_distance(x, y, metric))
+        assert (got[:, 150:] == -7.0).all()      # padding untouched
+
+
+def test_unaligned_output_falls_back_to_manual_stores():
+    x, y = blobs(130, 259, 32)
+    buf = torch.zeros(130 * 259 + 1, device="cuda")
+    out = buf[1:].view(130, 259)                  # 4-byte aligned only, odd row pitch
+    pairwise_distance(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), out=out, metric=DT.L2Expanded)
+    check(out.cpu().numpy(), oracle.pairwise_distance(x, y, DT.L2Expanded))
+
+
+@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.CosineExpanded, DT.L1, DT.Linf])
+def test_fortran_order(metric):
+    x, y = blobs(210, 170, 33)
+    xf = torch.from_numpy(x).cuda().t().contiguous().t()    # column-major storage
+    yf = torch.from_numpy(y).cuda().t().contiguous().t()
+    out = pairwise_distance(xf, yf, metric=metric)
+    got = out.copy_to_host()
+    assert got.shape == (210, 170)
+    check(got, oracle.pairwise_distance(x, y, metric))
+
+
+def test_fp16_inputs_tolerance_study():
+    """BASELINE.json configs[4] (fp16 in / fp32 accumulate): exact w.r.t. the fp16-rounded inputs,
+    ~1e-3 w.r.t. the original fp32 inputs."""
+    x, y = blobs(512, 384, 64)
+    xh, yh = x.astype(np.float16), y.astype(np.float16)
+    got = pairwise_distance(torch.from_numpy(xh).cuda(), torch.from_numpy(yh).cuda(), metric=DT.L2Expanded).copy_to_host()
+    check(got, oracle.pairwise_distance(xh, yh, DT.L2Expanded))
+    ref32 = oracle.pairwise_distance(x, y, DT.L2Expanded)
+    rel = np.abs(got - ref32) / np.maximum(ref32, 1e-6)
+    assert np.quantile(rel, 0.999) < 2e-2
+
+
+def test_output_conversion_and_handle():
+    x, y = blobs(64, 48, 16)
+    h = DeviceResources()
+    set_output_as("torch")
+    try:
+        out = pairwise_distance(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), metric="l1", handle=h)
+        h.sync()
+        assert isinstance(out, torch.Tensor)
+    finally:
+        set_output_as("raft")
+    out = pairwise_distance(device_ndarray(x), device_ndarray(y), metric="l1")
+    assert isinstance(out, device_ndarray)
+    check(out.copy_to_host(), oracle.pairwise_distance(x, y, DT.L1))
+
+
+def test_error_behaviour():
+    a = torch.zeros(4, 8, device="cuda"); b = torch.zeros(4, 9, device="cuda")
+    with pytest.raises(ValueError):
+        pairwise_distance(a, b)
+    with pytest.raises(ValueError):
+        pairwise_distance(a, a, metric="jaccard")
+    with pytest.raises(TypeError):
+        pairwise_distance(a, a.double())
+    with pytest.raises((ValueError, LogicError)):
+        pairwise_distance(a, a, metric="minkowski", p=0.0)
+    with pytest.raises(ValueError):
+        pairwise_distance(a, a, out=torch.zeros(3, 4, device="cuda"))
+    # empty problems are no-ops
+    out = pairwise_distance(torch.zeros(0, 8, device="cuda"), a)
+    assert out.shape == (0, 4)
+
+
+def test_full_size_sampled_check():
+    """Size-independent check at a BASELINE-scale shape: sample pairs of a 50000 x 40000 x 128
+    result and compare them with the oracle (the full matrix is 8 GB; the oracle sees 2e5 pairs)."""
+    m, n, k = 50000, 40000, 128
+    g = torch.Generator(device="cuda").manual_seed(7)
+    centers = (torch.rand(5, k, device="cuda", generator=g) * 20 - 10)
+    x = centers[torch.randint(0, 5, (m,), device="cuda", generator=g)] + torch.randn(m, k, device="cuda", generator=g)
+    y = centers[torch.randint(0, 5, (n,), device="cuda", generator=g)] + torch.randn(n, k, device="cuda", generator=g)
+    out = pairwise_distance(x, y, metric=DT.L2Expanded).tensor
+    ii = torch.randint(0, m, (200000,), device="cuda", generator=g)
+    jj = torch.randint(0, n, (200000,), device="cuda", generator=g)
+    # include tile corners / edges
+    ii[:4] = torch.tensor([0, m - 1, 0, m - 1], device="cuda"); jj[:4] = torch.tensor([0, n - 1, n - 1, 0], device="cuda")
+    got = out[ii, jj].cpu().numpy()
+    xs, ys = x[ii].cpu().numpy().astype(np.float64), y[jj].cpu().numpy().astype(np.float64)
+    ref = ((xs - ys) ** 2).sum(axis=1)
+    check(got, ref)
+    # every row block / column block was written (no stale tile): min over each 128x256 tile > 0
+    assert torch.isfinite(out).all()
+    assert (out.view(-1)[:: 104729] >= 0).all()
