@@ -210,8 +210,10 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
     return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
                     : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
-  // TMA tensor store needs a 16-byte aligned base and row pitch
-  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0);
+  // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
+  // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged
+  // widths take the manual store path
+  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0);
   if (getenv("B2D_NO_TMA_STORE")) tma = false;  // experiment knob
   { const char* e = getenv("B2D_ST_POLICY"); p.st_policy = e ? atoi(e) : 0; }
   if (tma) {

