@@ -1,0 +1,62 @@
+// Dependency-free C++ test of the header shim (GoogleTest is not on disk).
+// Compiled by tests/test_cpp_shim.py; runs on the GPU box, compiles (and links) everywhere.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+#include <raft/distance/fused_l2_nn.cuh>
+
+int main()
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::printf("SKIP no gpu\n"); return 0; }
+  const int m = 300, n = 200, k = 40;
+  std::vector<float> hx(m * k), hy(n * k);
+  for (int i = 0; i < m * k; ++i) hx[i] = std::sin(0.37f * i) * 3.f;
+  for (int i = 0; i < n * k; ++i) hy[i] = std::cos(0.11f * i) * 3.f;
+  float *x, *y, *d;
+  raft::KeyValuePair<int, float>* nn;
+  cudaMalloc(&x, hx.size() * 4); cudaMalloc(&y, hy.size() * 4); cudaMalloc(&d, m * n * 4);
+  cudaMalloc(&nn, m * sizeof(*nn));
+  cudaMemcpy(x, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(y, hy.data(), hy.size() * 4, cudaMemcpyHostToDevice);
+  cudaStream_t s;
+  cudaStreamCreate(&s);
+  int bad = 0;
+  {
+    raft::resources handle(s);
+    // legacy pointer API, as stats/detail/silhouette_score.cuh:205-206 calls it
+    raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::L2Unexpanded);
+    std::vector<float> h1(m * n), h2(m * n);
+    cudaMemcpyAsync(h1.data(), d, m * n * 4, cudaMemcpyDeviceToHost, s);
+    // mdspan API
+    auto xv = raft::make_device_matrix_view<const float, int>(x, m, k);
+    auto yv = raft::make_device_matrix_view<const float, int>(y, n, k);
+    auto dv = raft::make_device_matrix_view<float, int>(d, m, n);
+    raft::distance::pairwise_distance(handle, xv, yv, dv, raft::distance::DistanceType::L2Expanded);
+    cudaMemcpyAsync(h2.data(), d, m * n * 4, cudaMemcpyDeviceToHost, s);
+    raft::distance::fusedL2NNMinReduce<float, raft::KeyValuePair<int, float>, int>(nn, x, y, nullptr, nullptr, m, n, k,
+                                                                                    nullptr, false, true, handle);
+    std::vector<raft::KeyValuePair<int, float>> hn(m);
+    cudaMemcpyAsync(hn.data(), nn, m * sizeof(*nn), cudaMemcpyDeviceToHost, s);
+    raft::resource::sync_stream(handle);
+    for (int i = 0; i < m; ++i) {
+      int best = 0; double bv = 1e300;
+      for (int j = 0; j < n; ++j) {
+        double acc = 0;
+        for (int t = 0; t < k; ++t) { double df = (double)hx[i * k + t] - hy[j * k + t]; acc += df * df; }
+        if (std::fabs(h1[i * n + j] - acc) > 1e-4 * std::fmax(acc, 1.0)) ++bad;
+        if (std::fabs(h2[i * n + j] - acc) > 1e-4 * std::fmax(acc, 1.0)) ++bad;
+        if (acc < bv) { bv = acc; best = j; }
+      }
+      if (hn[i].key != best || std::fabs(hn[i].value - bv) > 1e-4 * std::fmax(bv, 1.0)) ++bad;
+    }
+    // error convention: unsupported metric -> raft::logic_error
+    bool threw = false;
+    try { raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::JaccardExpanded); }
+    catch (raft::logic_error const&) { threw = true; }
+    if (!threw) ++bad;
+  }
+  std::printf(bad ? "FAIL %d\n" : "PASS\n", bad);
+  return bad ? 1 : 0;
+}
