@@ -68,22 +68,6 @@ static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, in
   return B2D_OK;
 }
 
-// dist [m][n] fp32 (row pitch ldd), box = 32 x 32, SWIZZLE_128B (inner box = 128 bytes)
-static int make_dist_map(CUtensorMap* map, const float* base, int64_t m, int64_t n, int64_t ldd)
-{
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  cuuint64_t dims[2]    = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldd) * 4};
-  cuuint32_t box[2]     = {32, 32};
-  cuuint32_t estr[2]    = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(dist) failed: " + std::to_string((int)r));
-  return B2D_OK;
-}
-
 static int device_sms(int* sms, int* cc_major)
 {
   int dev = 0;
@@ -152,30 +136,24 @@ static int launch_prep(cudaStream_t s, const void* src, int64_t rs, int64_t cs, 
   return B2D_OK;
 }
 
-template <bool kRes, int kEpi, int kPost, bool kTma>
-static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                          const TcParams& p, int grid)
+template <bool kRes, int kEpi, int kPost>
+static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid)
 {
   // the attribute is per device and per function: cheap, set on every launch
-  B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost, kTma>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES)));
-  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, p);
+  B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(TC_SMEM_BYTES)));
+  expanded_tc_kernel<kRes, kEpi, kPost><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
 
 template <bool kRes>
-static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                           const TcParams& p, int grid, int post, bool tma)
+static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid,
+                           int post)
 {
-  if (tma) {
-    if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, true>(s, ma, mb, md, p, grid);
-    if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, true>(s, ma, mb, md, p, grid);
-    return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, true>(s, ma, mb, md, p, grid);
-  }
-  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, false>(s, ma, mb, md, p, grid);
-  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, false>(s, ma, mb, md, p, grid);
-  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, false>(s, ma, mb, md, p, grid);
+  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE>(s, ma, mb, p, grid);
+  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP>(s, ma, mb, p, grid);
+  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT>(s, ma, mb, p, grid);
 }
 
 static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post)
@@ -198,8 +176,7 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.xvec     = w.xvec;
   p.yvec     = w.yvec;
   if (p.n_items == 0) return B2D_OK;
-  CUtensorMap ma, mb, md;
-  memset(&md, 0, sizeof(md));
+  CUtensorMap ma, mb;
   rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
   if (rc) return rc;
   rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN);
@@ -207,21 +184,10 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   const int grid      = static_cast<int>(p.n_items < sms ? p.n_items : sms);
   const bool resident = p.nkb <= TC_MAX_RES_KB;
   if (epi == EPI_MINLOC) {
-    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
-                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
+    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE>(s, ma, mb, p, grid)
+                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE>(s, ma, mb, p, grid);
   }
-  // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
-  // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged
-  // widths take the manual store path
-  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0);
-  if (getenv("B2D_NO_TMA_STORE")) tma = false;  // experiment knob
-  { const char* e = getenv("B2D_ST_POLICY"); p.st_policy = e ? atoi(e) : 0; }
-  if (tma) {
-    rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
-    if (rc) return rc;
-  }
-  return resident ? launch_tc_store<true>(s, ma, mb, md, p, grid, post, tma)
-                  : launch_tc_store<false>(s, ma, mb, md, p, grid, post, tma);
+  return resident ? launch_tc_store<true>(s, ma, mb, p, grid, post) : launch_tc_store<false>(s, ma, mb, p, grid, post);
 }
 
 template <int kMetric>
@@ -334,7 +300,7 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     memset(&p, 0, sizeof(p));
     p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd;
     p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy) ? 1 : 0;
-    p.vec_ok    = (reinterpret_cast<uintptr_t>(dist) % 16 == 0 && ldd % 4 == 0) ? 1 : 0;
+    p.pair_ok   = (reinterpret_cast<uintptr_t>(dist) % 8 == 0 && ldd % 2 == 0) ? 1 : 0;
     return launch_tc(s, w, p, k, EPI_STORE, post);
   }
 

@@ -185,6 +185,25 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     : "r"(taddr)
     : "memory");
 }
+// TMEM -> registers, 16 lanes x 256 bits, x8: 16 rows x 64 fp32 columns per warp.  Fragment (the
+// m16n8 accumulator layout, repeated along columns): thread t holds, for i in [0,8):
+//   r[4i+0], r[4i+1] = row (t/4),     columns 8i + 2(t%4) + {0,1}
+//   r[4i+2], r[4i+3] = row (t/4) + 8, same columns
+// so a warp-wide 8-byte store of (r[4i], r[4i+1]) writes 8 rows x one full 32-byte sector.
+__device__ __forceinline__ void tmem_ld_16x256_x8(uint32_t taddr, uint32_t (&r)[32])
+{
+  asm volatile(
+    "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+      "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+      "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+      "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+      "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+    : "r"(taddr)
+    : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ descriptors
@@ -218,6 +237,10 @@ __device__ __forceinline__ void st_global_cs_v4(float* p, float4 v)
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
                : "memory");
+}
+__device__ __forceinline__ void st_global_cs_v2(float* p, float a, float b)
+{
+  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ void st_global_cs(float* p, float v)
 {
