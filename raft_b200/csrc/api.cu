@@ -82,9 +82,11 @@ static int device_sms(int* sms, int* cc_major)
 struct TcWorkspace {
   __half* xop;
   __half* yop;
-  float2* xvec;
-  float2* yvec;
+  float* xt;
+  float* yt;
   long long* keys;
+  unsigned* gmax;  // [2]
+  float* coef;     // [1]
   size_t bytes;
 };
 
@@ -99,11 +101,13 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   };
   char* c = static_cast<char*>(base);
   TcWorkspace w;
-  // xvec and keys come first so that their offsets depend on m only (b2d_fused_l2_nn_finalize
-  // finds |x_i|^2 again without knowing n or k)
-  w.xvec = reinterpret_cast<float2*>(c + take(static_cast<size_t>(m) * 8));
+  // scalars, xt and keys come first so that their offsets depend on m only
+  // (b2d_fused_l2_nn_finalize finds |x_i|^2 again without knowing n or k)
+  w.gmax = reinterpret_cast<unsigned*>(c + take(16));
+  w.coef = reinterpret_cast<float*>(w.gmax + 2);
+  w.xt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4));
   w.keys = reinterpret_cast<long long*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
-  w.yvec = reinterpret_cast<float2*>(c + take(static_cast<size_t>(n) * 8));
+  w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
   w.xop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(m) * nkb * 128));
   w.yop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(n) * nkb * 128));
   w.bytes = off;
@@ -122,16 +126,20 @@ static bool is_unexpanded(int metric)
 }
 
 template <typename T>
-static int launch_prep(cudaStream_t s, const void* src, int64_t rs, int64_t cs, int64_t rows, int64_t k,
-                       __half* op, float2* vec, const float* ext, int mode, int side, int center)
+static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int64_t xrs, int64_t xcs, int64_t m,
+                       const void* y, int64_t yrs, int64_t ycs, int64_t n, int64_t k, const float* xn, const float* yn,
+                       int mode, int center)
 {
-  if (rows == 0) return B2D_OK;
   PrepParams p;
-  p.src = src; p.rs = rs; p.cs = cs; p.rows = rows; p.k = static_cast<int>(k);
-  p.nkb = static_cast<int>((k + 31) / 32); p.op = op; p.vec = vec; p.ext_norm_sq = ext;
-  p.mode = mode; p.side = side; p.center = center;
-  const int64_t blocks = (rows + 7) / 8;
-  prep_rows_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
+  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, xn};
+  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, yn};
+  p.k = static_cast<int>(k); p.nkb = static_cast<int>((k + 31) / 32); p.mode = mode; p.center = center;
+  p.gmax = w.gmax; p.coef = w.coef;
+  B2D_CUDA(cudaMemsetAsync(w.gmax, 0, 16, s));
+  const int64_t blocks = (m + n + 7) / 8;
+  prep_max_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
+  B2D_CUDA(cudaGetLastError());
+  prep_split_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -173,8 +181,9 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.chunk    = static_cast<int>(chunk);
   p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
   p.n_items  = static_cast<int64_t>(p.tiles_n) * p.chunks_m;
-  p.xvec     = w.xvec;
-  p.yvec     = w.yvec;
+  p.xt       = w.xt;
+  p.yt       = w.yt;
+  p.coef     = w.coef;
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb;
   rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
@@ -285,16 +294,9 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     else if (metric == B2D_CosineExpanded) { mode = PREP_COSINE; }
     else if (metric == B2D_CorrelationExpanded) { mode = PREP_COSINE; center = 1; }
     else { mode = PREP_INNER; }
-    int rc;
-    if (dtype == B2D_F32) {
-      rc = launch_prep<float>(s, xa, xrs, xcs, ma, k, w.xop, w.xvec, nullptr, mode, 0, center);
-      if (rc) return rc;
-      rc = launch_prep<float>(s, ya, yrs, ycs, na, k, w.yop, w.yvec, nullptr, mode, 1, center);
-    } else {
-      rc = launch_prep<__half>(s, xa, xrs, xcs, ma, k, w.xop, w.xvec, nullptr, mode, 0, center);
-      if (rc) return rc;
-      rc = launch_prep<__half>(s, ya, yrs, ycs, na, k, w.yop, w.yvec, nullptr, mode, 1, center);
-    }
+    int rc = dtype == B2D_F32
+               ? launch_prep<float>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center)
+               : launch_prep<__half>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center);
     if (rc) return rc;
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -353,11 +355,9 @@ int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
     minloc_init_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), m);
     B2D_CUDA(cudaGetLastError());
   }
-  int rc = launch_prep<float>(s, x, ldx, 1, m, k, w.xop, w.xvec, xn, PREP_L2, 0, 0);
+  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, PREP_L2, 0);
   if (rc) return rc;
   if (n == 0) return B2D_OK;
-  rc = launch_prep<float>(s, y, ldy, 1, n, k, w.yop, w.yvec, yn, PREP_L2, 1, 0);
-  if (rc) return rc;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
@@ -371,10 +371,10 @@ int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys,
   if (m < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
   if (m == 0) return B2D_OK;
   if (!out || !keys || !workspace) return fail(B2D_ERR_INVALID_ARG, "null out / keys / workspace");
-  if (workspace_bytes < static_cast<size_t>(m) * 8) return fail(B2D_ERR_WORKSPACE, "workspace too small");
+  if (workspace_bytes < 1024 + static_cast<size_t>(m) * 4) return fail(B2D_ERR_WORKSPACE, "workspace too small");
   TcWorkspace w = tc_layout(const_cast<void*>(workspace), m, 0, 0, true);
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
-    reinterpret_cast<KvpIF*>(out), reinterpret_cast<const long long*>(keys), w.xvec, m, do_sqrt, 0);
+    reinterpret_cast<KvpIF*>(out), reinterpret_cast<const long long*>(keys), w.xt, m, do_sqrt, 0);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -395,7 +395,7 @@ int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, 
                                 workspace, workspace_bytes);
   if (rc) return rc;
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
-    reinterpret_cast<KvpIF*>(out), w.keys, w.xvec, m, do_sqrt, init_out ? 0 : 1);
+    reinterpret_cast<KvpIF*>(out), w.keys, w.xt, m, do_sqrt, init_out ? 0 : 1);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }

@@ -33,7 +33,7 @@
 // group (the m16n8 fragment), so results go from registers STRAIGHT to global memory: a warp-wide
 // 8-byte store writes 8 rows x one full 32-byte sector -- no shared-memory staging (shared-memory
 // bandwidth is the scarce resource: tcgen05.mma reads its operands from it at up to 128 B/clk).
-//   d = acc * (a.x*b.x) + (a.y+b.y) on packed f32x2 pipes (FMUL2/FADD2/FFMA2), then
+//   d = acc * c + (t_x[i] + t_y[j]) on packed f32x2 pipes (FADD2/FFMA2; c is one scalar), then
 //   EPI_STORE   clamp / sqrt / st.global.cs.v2
 //   EPI_MINLOC  per-row running min / arg-min (FMNMX3 tree per 16 values, rare index rescan), quad
 //               shuffle reduce, one packed 64-bit atomicMin per row per 128 columns, skipped when
@@ -67,8 +67,9 @@ struct TcParams {
   int chunk;              // m-tiles per work item
   int chunks_m;           // ceil(tiles_m/chunk)
   int64_t n_items;        // tiles_n * chunks_m
-  const float2* xvec;     // [m] (a.x, a.y)
-  const float2* yvec;     // [n] (b.x, b.y)
+  const float* xt;        // [m] row term t_x[i]
+  const float* yt;        // [n] column term t_y[j]
+  const float* coef;      // [1] scalar c: d = acc * c + (t_x[i] + t_y[j])  (prep.cuh)
   // EPI_STORE
   float* dist;
   int64_t ldd;
@@ -81,7 +82,7 @@ struct TcParams {
 
 constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES_RES * TC_A_BYTES;  // 224 KB
 static_assert((size_t)TC_STAGES_STR * (TC_A_BYTES + TC_B_BYTES) <= TC_SMEM_OPERANDS, "streaming carve fits");
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + 2 * TC_BN * 4 + 256;
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_BN * 4 + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
 
 // float -> int whose signed order equals the float order
@@ -145,8 +146,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* b_base = smem;  // resident slabs, or per-stage B
   uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES_STR * TC_B_BYTES);
-  float* col_cb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);  // [256] b.x
-  float* col_tb   = col_cb + TC_BN;                                     // [256] b.y
+  float* col_tb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);  // [256] t_y of this y block
   uint64_t* bars  = reinterpret_cast<uint64_t*>(col_tb + TC_BN);
   uint64_t* afull = bars;                       // [TC_MAX_STAGES]
   uint64_t* aempty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
@@ -301,19 +301,20 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int quad = lane >> 2;         // fragment row inside a 16-row group (and +8)
     const int tq   = lane & 3;          // fragment column pair inside an 8-column group
     uint32_t t_it  = 0;
+    const float cf     = __ldg(p.coef);
+    const uint64_t cf2 = pk(cf, cf);
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n_blk = static_cast<int>(item % p.tiles_n);
       const int ch    = static_cast<int>(item / p.tiles_n);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
-      // per-column epilogue pairs of this y block (shared by every tile of the item)
+      // per-column epilogue terms of this y block (shared by every tile of the item)
       ptx::bar_sync(1, 32 * TC_EPI_WARPS);
       {
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
-        float2 cv        = make_float2(0.f, kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f);
-        if (gj < p.n) cv = __ldg(&p.yvec[gj]);
-        col_cb[et] = cv.x;
-        col_tb[et] = cv.y;
+        float tv = kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f;  // +inf: never the arg-min
+        if (gj < p.n) tv = __ldg(&p.yt[gj]);
+        col_tb[et] = tv;
       }
       ptx::bar_sync(1, 32 * TC_EPI_WARPS);
       const int64_t col0 = static_cast<int64_t>(n_blk) * TC_BN + g * 128;  // first global column of this warp
@@ -322,20 +323,19 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
         // the 4 tile rows this thread owns: 32q + quad + 8j, j = 0..3  (j = 2*rh + (0|1))
         const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;
-        uint64_t ra2[4], ta2[4];
+        uint64_t ta2[4];
         long long cur_key[4];
         float best_v[4];
         int best_j[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 rv  = make_float2(0.f, 0.f);
+          float rv   = 0.f;
           cur_key[j] = 0x7FFFFFFFFFFFFFFFll;
           if (row0 + 8 * j < p.m) {
-            rv = __ldg(&p.xvec[row0 + 8 * j]);
+            rv = __ldg(&p.xt[row0 + 8 * j]);
             if (kEpi == EPI_MINLOC && tq == 0) cur_key[j] = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
           }
-          ra2[j]    = pk(rv.x, rv.x);
-          ta2[j]    = pk(rv.y, rv.y);
+          ta2[j]    = pk(rv, rv);
           best_v[j] = __int_as_float(0x7f800000);
           best_j[j] = 0x7fffffff;
         }
@@ -368,14 +368,13 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int cl0 = g * 128 + cc * 64 + 2 * tq;  // this thread's first column inside the tile
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float2 cb = *reinterpret_cast<const float2*>(&col_cb[cl0 + 8 * i]);
             const float2 tb = *reinterpret_cast<const float2*>(&col_tb[cl0 + 8 * i]);
             uint64_t a0 = pk(r[4 * i], r[4 * i + 1]), a1 = pk(r[4 * i + 2], r[4 * i + 3]);
             if (!kResident) {
               a0 = add2(a0, pk(rc[4 * i], rc[4 * i + 1]));
               a1 = add2(a1, pk(rc[4 * i + 2], rc[4 * i + 3]));
             }
-            const uint64_t cb2 = pk(cb.x, cb.y), tb2 = pk(tb.x, tb.y);
+            const uint64_t tb2 = pk(tb.x, tb.y);
             uint64_t t0, t1;
             if (kEpi == EPI_STORE) {
               t0 = add2(ta2[2 * rh], tb2);
@@ -384,8 +383,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               t0 = tb2;
               t1 = tb2;
             }
-            unpk(fma2(a0, mul2(ra2[2 * rh], cb2), t0), v[4 * i], v[4 * i + 1]);
-            unpk(fma2(a1, mul2(ra2[2 * rh + 1], cb2), t1), v[4 * i + 2], v[4 * i + 3]);
+            unpk(fma2(a0, cf2, t0), v[4 * i], v[4 * i + 1]);
+            unpk(fma2(a1, cf2, t1), v[4 * i + 2], v[4 * i + 3]);
           }
           if (f < 3) {  // r / rc are dead: fetch the next fragment while this one is stored / reduced
             const int nf       = f + 1;
@@ -513,7 +512,7 @@ struct KvpIF {
 
 // packed key -> raft::KeyValuePair<int,float>{argmin, min distance}; adds the row-constant
 // |x_i|^2 that the pair loop leaves out, clamps at 0, optional sqrt.
-__global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const float2* xvec,
+__global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const float* xt,
                                        int64_t m, int do_sqrt, int merge_existing)
 {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -522,7 +521,7 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const 
   int s               = static_cast<int>(key >> 32);
   int bits            = s < 0 ? (s ^ 0x7FFFFFFF) : s;
   float v             = __int_as_float(bits);
-  float d             = fmaxf(xvec[i].y + v, 0.f);
+  float d             = fmaxf(xt[i] + v, 0.f);
   if (do_sqrt) d = sqrtf(d);
   KvpIF o;
   o.key   = static_cast<int>(key & 0xFFFFFFFFll);
