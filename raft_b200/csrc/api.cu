@@ -144,24 +144,41 @@ static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int6
   return B2D_OK;
 }
 
-template <bool kRes, int kEpi, int kPost>
-static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid)
+// dist [m][n] fp32 (row pitch ldd), box = 32 x 32, SWIZZLE_128B (inner box = 128 bytes)
+static int make_dist_map(CUtensorMap* map, const float* base, int64_t m, int64_t n, int64_t ldd)
+{
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2]    = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldd) * 4};
+  cuuint32_t box[2]     = {32, 32};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(dist) failed: " + std::to_string((int)r));
+  return B2D_OK;
+}
+
+template <bool kRes, int kEpi, int kPost, bool kTma>
+static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                          const TcParams& p, int grid)
 {
   // the attribute is per device and per function: cheap, set on every launch
-  B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(TC_SMEM_BYTES)));
-  expanded_tc_kernel<kRes, kEpi, kPost><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, p);
+  B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost, kTma>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES)));
+  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
 
-template <bool kRes>
-static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int grid,
-                           int post)
+template <bool kRes, bool kTma>
+static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                           const TcParams& p, int grid, int post)
 {
-  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE>(s, ma, mb, p, grid);
-  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP>(s, ma, mb, p, grid);
-  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT>(s, ma, mb, p, grid);
+  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, kTma>(s, ma, mb, md, p, grid);
+  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, kTma>(s, ma, mb, md, p, grid);
+  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, kTma>(s, ma, mb, md, p, grid);
 }
 
 static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post)
@@ -185,7 +202,8 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.yt       = w.yt;
   p.coef     = w.coef;
   if (p.n_items == 0) return B2D_OK;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, md;
+  memset(&md, 0, sizeof(md));
   rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
   if (rc) return rc;
   rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN);
@@ -193,10 +211,23 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   const int grid      = static_cast<int>(p.n_items < sms ? p.n_items : sms);
   const bool resident = p.nkb <= TC_MAX_RES_KB;
   if (epi == EPI_MINLOC) {
-    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE>(s, ma, mb, p, grid)
-                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE>(s, ma, mb, p, grid);
+    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
+                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
-  return resident ? launch_tc_store<true>(s, ma, mb, p, grid, post) : launch_tc_store<false>(s, ma, mb, p, grid, post);
+  // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
+  // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
+  // unaligned outputs take the direct register->global path
+  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0);
+  if (getenv("B2D_NO_TMA_STORE")) tma = false;  // experiment knob
+  { const char* e = getenv("B2D_STORE_MIX"); p.store_mix = e ? atoi(e) : 0; }
+  if (tma) {
+    rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
+    if (rc) return rc;
+    return resident ? launch_tc_store<true, true>(s, ma, mb, md, p, grid, post)
+                    : launch_tc_store<false, true>(s, ma, mb, md, p, grid, post);
+  }
+  return resident ? launch_tc_store<true, false>(s, ma, mb, md, p, grid, post)
+                  : launch_tc_store<false, false>(s, ma, mb, md, p, grid, post);
 }
 
 template <int kMetric>

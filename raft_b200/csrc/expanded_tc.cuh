@@ -75,6 +75,7 @@ struct TcParams {
   int64_t ldd;
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
   int pair_ok;            // dist 8-byte aligned and ldd even -> st.v2
+  int store_mix;          // kTma: 1 = odd 32-column chunks leave through LSU stores, even through TMA
   // EPI_MINLOC
   long long* keys;        // [m] packed (ordered float bits << 32 | index)
   int64_t idx_offset;
@@ -134,18 +135,22 @@ __device__ __forceinline__ float min3(float a, float b, float c)
   return r;
 }
 
-template <bool kResident, int kEpi, int kPost>
+template <bool kResident, int kEpi, int kPost, bool kTma>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const TcParams p)
+                   const __grid_constant__ CUtensorMap tmap_d, const TcParams p)
 {
-  constexpr int kStages = kResident ? TC_STAGES_RES : TC_STAGES_STR;
+  // kTma (EPI_STORE only): results leave through a swizzled shared-memory staging block and one TMA
+  // tensor store per warp per 32 columns (whole 128-byte lines); the 32 KB of staging replace two
+  // of the six x stages.
+  constexpr int kStages = kResident ? (kTma ? TC_STAGES_RES - 2 : TC_STAGES_RES) : TC_STAGES_STR;
   extern __shared__ __align__(1024) uint8_t smem[];
   // SWIZZLE_128B atoms need 1024-byte alignment; the dynamic window starts 1024-aligned (no static
   // shared memory in this kernel).  Checked, not assumed: a misaligned base traps.
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* b_base = smem;  // resident slabs, or per-stage B
   uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES_STR * TC_B_BYTES);
+  float* stg      = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS - TC_EPI_WARPS * 4096);  // kTma only
   float* col_tb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);  // [256] t_y of this y block
   uint64_t* bars  = reinterpret_cast<uint64_t*>(col_tb + TC_BN);
   uint64_t* afull = bars;                       // [TC_MAX_STAGES]
@@ -166,6 +171,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (kTma) ptx::prefetch_tmap(&tmap_d);
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
@@ -302,6 +308,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int tq   = lane & 3;          // fragment column pair inside an 8-column group
     uint32_t t_it  = 0;
     const float cf     = __ldg(p.coef);
+    const uint64_t pol_st = ptx::policy_evict_first();
     const uint64_t cf2 = pk(cf, cf);
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n_blk = static_cast<int>(item % p.tiles_n);
@@ -321,6 +328,102 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool cols_in = col0 + 127 < p.n;
 
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
+        if (kTma) {
+          // ---------------- EPI_STORE through shared memory + TMA tensor store ----------------
+          uint32_t tb_idx, tph;
+          if (kResident) { tb_idx = t_it & 1; tph = (t_it >> 1) & 1; }
+          else { tb_idx = g; tph = t_it & 1; }
+          const int64_t gi = static_cast<int64_t>(mt) * TC_BM + q * 32 + lane;  // thread == output row
+          float tav        = 0.f;
+          if (gi < p.m) tav = __ldg(&p.xt[gi]);
+          const uint64_t tav2 = pk(tav, tav);
+          // k <= 96 leaves the 4th y slab unused: a second staging block per warp lets the TMA store
+          // of chunk c overlap the staging of chunk c+1
+          const bool dbuf     = kResident && nkb <= 3;
+          float* stg_a        = stg + (warp - 2) * 1024;
+          float* stg_b        = dbuf ? reinterpret_cast<float*>(b_base + 3 * TC_B_BYTES) + (warp - 2) * 1024 : stg_a;
+          ptx::mbar_wait(&tfull[tb_idx], tph);
+          ptx::tc_fence_after();
+          const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                  (kResident ? (t_it & 1) * TC_BN + g * 128 : g * 256);
+          uint32_t r[32], rc[32];
+          ptx::tmem_ld_32x32(t_base, r);
+          if (!kResident) ptx::tmem_ld_32x32(t_base + 128, rc);
+#pragma unroll 1
+          for (int chunk = 0; chunk < 4; ++chunk) {
+            const int cbase = g * 128 + chunk * 32;
+            ptx::tmem_ld_wait();
+            if (chunk == 3) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tempty[tb_idx]);
+            }
+            float v[32];
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 tb = *reinterpret_cast<const float4*>(&col_tb[cbase + c]);
+              uint64_t a0 = pk(r[c], r[c + 1]), a1 = pk(r[c + 2], r[c + 3]);
+              if (!kResident) {
+                a0 = add2(a0, pk(rc[c], rc[c + 1]));
+                a1 = add2(a1, pk(rc[c + 2], rc[c + 3]));
+              }
+              unpk(fma2(a0, cf2, add2(tav2, pk(tb.x, tb.y))), v[c], v[c + 1]);
+              unpk(fma2(a1, cf2, add2(tav2, pk(tb.z, tb.w))), v[c + 2], v[c + 3]);
+            }
+            if (chunk < 3) {
+              ptx::tmem_ld_32x32(t_base + (chunk + 1) * 32, r);
+              if (!kResident) ptx::tmem_ld_32x32(t_base + (chunk + 1) * 32 + 128, rc);
+            }
+            const int64_t gj0 = static_cast<int64_t>(n_blk) * TC_BN + cbase;
+            if (kPost != POST_NONE) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+              if (p.diag_zero && gi >= gj0 && gi < gj0 + 32) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (gi == gj0 + c) v[c] = 0.f;
+              }
+              if (kPost == POST_CLAMP_SQRT) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) asm("sqrt.approx.f32 %0, %1;" : "=f"(v[c]) : "f"(v[c]));
+              }
+            }
+            // 16-byte chunks XOR-swizzled by (row & 7): conflict-free, and exactly SWIZZLE_128B
+            float* my_stg = (chunk & 1) ? stg_b : stg_a;
+            if (lane == 0) {  // the previous store out of this buffer has left it
+              if (dbuf) ptx::tma_store_wait_read1();
+              else ptx::tma_store_wait_read();
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              *reinterpret_cast<float4*>(my_stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+                make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            if (p.store_mix && (chunk & 1)) {
+              // second store engine: the LSU.  4 rows x 128 bytes per instruction, straight from
+              // the staging block (runs concurrently with the TMA stores of the even chunks)
+              __syncwarp();
+              const int c4 = lane & 7;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr      = it * 4 + (lane >> 3);
+                const float4 o    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
+                const int64_t gj  = gj0 + c4 * 4;
+                if (gi2 < p.m && gj < p.n) ptx::st_global_cs_v4(p.dist + gi2 * p.ldd + gj, o);
+              }
+              __syncwarp();
+            } else {
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::tma_store_2d(&tmap_d, my_stg, static_cast<int32_t>(gj0), mt * TC_BM + q * 32, pol_st);
+                ptx::tma_store_commit();
+              }
+            }
+          }
+          continue;
+        }
         // the 4 tile rows this thread owns: 32q + quad + 8j, j = 0..3  (j = 2*rh + (0|1))
         const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;
         uint64_t ta2[4];
@@ -488,6 +591,10 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   }
 
+  if (kTma && warp >= 2) {
+    if (lane == 0) ptx::tma_store_wait_all();
+    __syncwarp();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
