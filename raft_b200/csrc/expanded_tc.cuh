@@ -427,20 +427,21 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // the 4 tile rows this thread owns: 32q + quad + 8j, j = 0..3  (j = 2*rh + (0|1))
         const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;
         uint64_t ta2[4];
-        long long cur_key[4];
-        float best_v[4];
-        int best_j[4];
+        float thr[4];  // EPI_MINLOC: value of the row's current global best (an upper bound: keys only decrease)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float rv   = 0.f;
-          cur_key[j] = 0x7FFFFFFFFFFFFFFFll;
+          float rv = 0.f;
+          thr[j]   = __int_as_float(0xff800000);  // -inf: rows outside the matrix never trigger
           if (row0 + 8 * j < p.m) {
-            rv = __ldg(&p.xt[row0 + 8 * j]);
-            if (kEpi == EPI_MINLOC && tq == 0) cur_key[j] = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
+            if (kEpi == EPI_STORE) rv = __ldg(&p.xt[row0 + 8 * j]);
+            if (kEpi == EPI_MINLOC) {
+              const long long ck = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
+              const int sb       = static_cast<int>(ck >> 32);
+              thr[j]             = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);  // +max key -> NaN-free +inf-ish
+              if (ck == 0x7FFFFFFFFFFFFFFFll) thr[j] = __int_as_float(0x7f800000);
+            }
           }
-          ta2[j]    = pk(rv, rv);
-          best_v[j] = __int_as_float(0x7f800000);
-          best_j[j] = 0x7fffffff;
+          ta2[j] = pk(rv, rv);
         }
         const bool rows_in = static_cast<int64_t>(mt) * TC_BM + q * 32 + 31 < p.m;
 
@@ -538,52 +539,40 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               }
             }
           } else {
-            // per row: min of this thread's 16 values with 3-input FMNMX, then (rarely) locate it.
-            // Ascending scan with '==' keeps the smallest column on ties, strict '<' against the
-            // running best keeps the earliest chunk (raft::argmin_op,
-            // cpp/include/raft/core/operators.hpp:187-194)
+            // per row: min of this thread's 16 values with 3-input FMNMX, compared with the row's
+            // current global best.  Only a candidate that can change the result (value <= best:
+            // '<=' so that an equal value with a smaller index still gets through) takes the slow
+            // path: locate the smallest column holding the minimum (ascending scan) and let the
+            // packed 64-bit atomicMin decide -- (value, index) order == raft::argmin_op
+            // (cpp/include/raft/core/operators.hpp:187-194).  After the first few y blocks this is rare,
+            // so the common path is FFMA2 + FMNMX3 + one warp vote per row.
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
               const int o = 2 * rr;
-              float mn    = min3(v[o], v[o + 1], v[4 + o]);
-              mn          = min3(mn, v[4 + o + 1], v[8 + o]);
-              mn          = min3(mn, v[8 + o + 1], v[12 + o]);
-              mn          = min3(mn, v[12 + o + 1], v[16 + o]);
-              mn          = min3(mn, v[16 + o + 1], v[20 + o]);
-              mn          = min3(mn, v[20 + o + 1], v[24 + o]);
-              mn          = min3(mn, v[24 + o + 1], v[28 + o]);
-              mn          = fminf(mn, v[28 + o + 1]);
-              const int j = 2 * rh + rr;
-              if (mn < best_v[j]) {
-                best_v[j] = mn;
-                int cbest = 0;
+              float m0    = min3(v[o], v[o + 1], v[4 + o]);
+              float m1    = min3(v[4 + o + 1], v[8 + o], v[8 + o + 1]);
+              float m2    = min3(v[12 + o], v[12 + o + 1], v[16 + o]);
+              float m3    = min3(v[16 + o + 1], v[20 + o], v[20 + o + 1]);
+              m0          = min3(m0, v[24 + o], v[24 + o + 1]);
+              m1          = min3(m1, v[28 + o], v[28 + o + 1]);
+              const float mn = fminf(min3(m0, m1, m2), m3);
+              const int j    = 2 * rh + rr;
+              // (+inf marks columns beyond n: never a candidate)
+              const bool cand = mn <= thr[j] && mn < __int_as_float(0x7f800000);
+              if (__any_sync(0xffffffffu, cand)) {
+                if (cand) {
+                  int cbest = 0;
 #pragma unroll
-                for (int i = 7; i >= 0; --i) {
-                  if (v[4 * i + o + 1] == mn) cbest = 8 * i + 1;
-                  if (v[4 * i + o] == mn) cbest = 8 * i;
+                  for (int i = 7; i >= 0; --i) {
+                    if (v[4 * i + o + 1] == mn) cbest = 8 * i + 1;
+                    if (v[4 * i + o] == mn) cbest = 8 * i;
+                  }
+                  const long long gj  = static_cast<long long>(n_blk) * TC_BN + cl0 + cbest + p.idx_offset;
+                  const long long key = (static_cast<long long>(ordered_bits(mn)) << 32) | (gj & 0xFFFFFFFFll);
+                  atomicMin(&p.keys[row0 + 8 * j], key);
+                  thr[j] = mn;
                 }
-                best_j[j] = cl0 + cbest;
               }
-            }
-          }
-        }
-        if (kEpi == EPI_MINLOC) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // the 4 lanes of a quad hold interleaved columns of the same row: lexicographic
-            // (value, column) min across them
-            float bv = best_v[j];
-            int bj   = best_j[j];
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-              const int oj   = __shfl_xor_sync(0xffffffffu, bj, o);
-              if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
-            }
-            if (tq == 0 && row0 + 8 * j < p.m && bj != 0x7fffffff) {
-              const long long gj  = static_cast<long long>(n_blk) * TC_BN + bj + p.idx_offset;
-              const long long key = (static_cast<long long>(ordered_bits(bv)) << 32) | (gj & 0xFFFFFFFFll);
-              if (key < cur_key[j]) atomicMin(&p.keys[row0 + 8 * j], key);
             }
           }
         }
