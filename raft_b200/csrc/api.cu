@@ -218,8 +218,6 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
   // unaligned outputs take the direct register->global path
   bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0);
-  if (getenv("B2D_NO_TMA_STORE")) tma = false;  // experiment knob
-  { const char* e = getenv("B2D_STORE_MIX"); p.store_mix = e ? atoi(e) : 0; }
   if (tma) {
     rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
     if (rc) return rc;
@@ -230,9 +228,37 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
                   : launch_tc_store<false, false>(s, ma, mb, md, p, grid, post);
 }
 
+// fp32 row-major matrix [rows][k] with row pitch ld: box = 32 floats x 128 rows, SWIZZLE_128B
+static int make_f32_map(CUtensorMap* map, const float* base, int64_t rows, int64_t k, int64_t ld)
+{
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2]    = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2]     = {UX_KB, UX_BM};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(f32 operand) failed: " + std::to_string((int)r));
+  return B2D_OK;
+}
+
 template <int kMetric>
 static int launch_ux_inst(cudaStream_t s, const UxParams& p, int64_t tiles)
 {
+  if (p.vec_x && p.vec_y) {  // TMA-legal operands: hardware-staged tiles
+    CUtensorMap mx, my;
+    int rc = make_f32_map(&mx, p.x, p.m, p.k, p.xrs);
+    if (rc) return rc;
+    rc = make_f32_map(&my, p.y, p.n, p.k, p.yrs);
+    if (rc) return rc;
+    B2D_CUDA(cudaFuncSetAttribute(unexpanded_tma_kernel<kMetric>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  UX_TMA_SMEM_BYTES));
+    unexpanded_tma_kernel<kMetric><<<static_cast<unsigned>(tiles), UX_THREADS, UX_TMA_SMEM_BYTES, s>>>(mx, my, p);
+    B2D_CUDA(cudaGetLastError());
+    return B2D_OK;
+  }
   cudaError_t e = cudaFuncSetAttribute(unexpanded_simt_kernel<kMetric>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        UX_SMEM_BYTES);
   B2D_CUDA(e);

@@ -75,7 +75,6 @@ struct TcParams {
   int64_t ldd;
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
   int pair_ok;            // dist 8-byte aligned and ldd even -> st.v2
-  int store_mix;          // kTma: 1 = odd 32-column chunks leave through LSU stores, even through TMA
   // EPI_MINLOC
   long long* keys;        // [m] packed (ordered float bits << 32 | index)
   int64_t idx_offset;
@@ -399,21 +398,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int c4 = 0; c4 < 8; ++c4)
               *reinterpret_cast<float4*>(my_stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
                 make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-            if (p.store_mix && (chunk & 1)) {
-              // second store engine: the LSU.  4 rows x 128 bytes per instruction, straight from
-              // the staging block (runs concurrently with the TMA stores of the even chunks)
-              __syncwarp();
-              const int c4 = lane & 7;
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int rr      = it * 4 + (lane >> 3);
-                const float4 o    = *reinterpret_cast<const float4*>(my_stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-                const int64_t gi2 = static_cast<int64_t>(mt) * TC_BM + q * 32 + rr;
-                const int64_t gj  = gj0 + c4 * 4;
-                if (gi2 < p.m && gj < p.n) ptx::st_global_cs_v4(p.dist + gi2 * p.ldd + gj, o);
-              }
-              __syncwarp();
-            } else {
+            {
               ptx::fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {

@@ -11,13 +11,17 @@
 // registers while the current one is consumed (software pipelining, double-buffered smem).
 // Bound: FP32 pipe (>= 2 lane-ops per pair-element), not HBM -- see DESIGN.md.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "ptx.cuh"
 
 namespace b2d {
 
 constexpr int UX_BM = 128, UX_BN = 128, UX_KB = 32, UX_THREADS = 256;
 constexpr int UX_SMEM_BYTES = 2 * (UX_BM + UX_BN) * UX_KB * 4;
+constexpr int UX_TMA_STAGES = 3;
+constexpr int UX_TMA_SMEM_BYTES = UX_TMA_STAGES * (UX_BM + UX_BN) * UX_KB * 4 + 64;
 
 enum UxMetric : int { UX_L1 = 0, UX_L2 = 1, UX_L2SQRT = 2, UX_LINF = 3, UX_CANBERRA = 4, UX_LP = 5 };
 
@@ -45,10 +49,14 @@ __device__ __forceinline__ void ux_acc(float& acc, float a, float b, float p)
   } else if (kMetric == UX_LINF) {
     acc = fmaxf(acc, fabsf(a - b));
   } else if (kMetric == UX_CANBERRA) {
+    // |a-b| / (|a|+|b|), 0/0 -> 0 (scipy / reference convention).  s == 0 implies d == 0, so
+    // clamping s away from zero turns the special case into 0 * finite = 0 without a select;
+    // one MUFU.RCP per element makes this metric MUFU-bound (16 lanes/clk/SM).
     const float d = fabsf(a - b);
-    const float s = fabsf(a) + fabsf(b);
-    // 0/0 -> 0 (scipy / reference convention); s == 0 implies d == 0
-    acc += (s == 0.f) ? 0.f : __fdividef(d, s);
+    const float s = fmaxf(fabsf(a) + fabsf(b), 1e-30f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    acc = fmaf(d, r, acc);
   } else {
     const float d = fabsf(a - b);
     acc += exp2f(p * __log2f(d));  // d == 0 -> log2 = -inf -> exp2 = 0
@@ -154,6 +162,94 @@ __global__ void __launch_bounds__(UX_THREADS, 1) unexpanded_simt_kernel(const Ux
       sstore(buf ^ 1);
       __syncthreads();
     }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gi = m0 + ty + 16 * i;
+    if (gi >= p.m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t gj = n0 + tx + 16 * j;
+      if (gj < p.n) __stcs(p.dist + gi * p.ldd + gj, ux_fin<kMetric>(acc[i][j], p.inv_p));
+    }
+  }
+}
+
+// TMA-fed variant (rows 16-byte aligned, k % 4 == 0, row-major): the same 128x128x32 tiles arrive
+// by cp.async.bulk.tensor with SWIZZLE_128B -- the XOR pattern the manual loader writes -- through
+// a 3-stage mbarrier ring, so no thread spends registers or issue slots on staging and OOB rows /
+// k tails are zero-filled by the hardware.  One elected thread issues; all 256 threads compute.
+template <int kMetric>
+__global__ void __launch_bounds__(UX_THREADS, 1)
+unexpanded_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                      const UxParams p)
+{
+  extern __shared__ __align__(1024) uint8_t ux_raw[];
+  if ((ptx::smem_u32(ux_raw) & 1023u) != 0u) __trap();
+  constexpr int kTile = UX_BM * UX_KB;  // floats per operand tile
+  float* sx       = reinterpret_cast<float*>(ux_raw);
+  float* sy       = sx + UX_TMA_STAGES * kTile;
+  uint64_t* full  = reinterpret_cast<uint64_t*>(sy + UX_TMA_STAGES * kTile);
+
+  const int tid = threadIdx.x;
+  const int tx  = tid & 15;
+  const int ty  = tid >> 4;
+  const int64_t tile = blockIdx.x;
+  const int m0       = static_cast<int>(tile / p.tiles_n) * UX_BM;
+  const int n0       = static_cast<int>(tile % p.tiles_n) * UX_BN;
+  const int nkb      = (p.k + UX_KB - 1) / UX_KB;
+
+  if (tid == 0) {
+    for (int i = 0; i < UX_TMA_STAGES; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  const uint64_t pol = ptx::policy_evict_last();
+  auto issue = [&](int kb) {
+    const int s = kb % UX_TMA_STAGES;
+    ptx::mbar_expect_tx(&full[s], 2 * kTile * 4);
+    ptx::tma_load_2d(sx + s * kTile, &tmap_x, &full[s], kb * UX_KB, m0, pol);
+    ptx::tma_load_2d(sy + s * kTile, &tmap_y, &full[s], kb * UX_KB, n0, pol);
+  };
+  if (tid == 0)
+    for (int kb = 0; kb < UX_TMA_STAGES - 1 && kb < nkb; ++kb) issue(kb);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % UX_TMA_STAGES;
+    ptx::mbar_wait(&full[s], (kb / UX_TMA_STAGES) & 1);
+    const float* bx = sx + s * kTile;
+    const float* by = sy + s * kTile;
+#pragma unroll 2
+    for (int c4 = 0; c4 < 8; ++c4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = ty + 16 * i;
+        a[i] = *reinterpret_cast<const float4*>(&bx[row * UX_KB + ((c4 ^ (row & 7)) << 2)]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row  = tx + 16 * j;
+        const float4 b = *reinterpret_cast<const float4*>(&by[row * UX_KB + ((c4 ^ (row & 7)) << 2)]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ux_acc<kMetric>(acc[i][j], a[i].x, b.x, p.p);
+          ux_acc<kMetric>(acc[i][j], a[i].y, b.y, p.p);
+          ux_acc<kMetric>(acc[i][j], a[i].z, b.z, p.p);
+          ux_acc<kMetric>(acc[i][j], a[i].w, b.w, p.p);
+        }
+      }
+    }
+    // every thread is done with the stage that block kb-1 used: refill it with block kb+STAGES-1
+    __syncthreads();
+    if (tid == 0 && kb + UX_TMA_STAGES - 1 < nkb) issue(kb + UX_TMA_STAGES - 1);
   }
 
 #pragma unroll

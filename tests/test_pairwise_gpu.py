@@ -71,6 +71,36 @@ def test_uniform_data(metric):
     check(run(x, y, metric), oracle.pairwise_distance(x, y, metric))
 
 
+def test_canberra_zero_over_zero_is_zero():
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((150, 40)).astype(np.float32)
+    y = rng.standard_normal((130, 40)).astype(np.float32)
+    x[:, ::3] = 0.0
+    y[:, ::3] = 0.0          # shared zero coordinates: 0/0 terms must contribute 0, not NaN
+    x[7] = 0.0
+    y[11] = 0.0              # a fully-zero pair
+    got = run(x, y, DT.Canberra)
+    assert np.isfinite(got).all() and got[7, 11] == 0.0
+    check(got, oracle.pairwise_distance(x, y, DT.Canberra))
+
+
+@pytest.mark.parametrize("k", [32, 64, 96, 128, 160, 288])
+def test_every_k_regime_of_the_tensor_kernel(k):
+    # k <= 96: double-buffered staging; k <= 128: resident y block; k > 128: streaming operands
+    x, y = blobs(515, 1028, k, seed=k)
+    for metric in (DT.L2Expanded, DT.CosineExpanded):
+        check(run(x, y, metric), oracle.pairwise_distance(x, y, metric))
+
+
+def test_wide_dynamic_range_rows():
+    # one power-of-two scale per matrix: rows 2^12 below the matrix maximum keep full precision
+    x, y = blobs(300, 260, 64)
+    x[::2] *= 2.0 ** -12
+    y[::3] *= 2.0 ** -12
+    check(run(x, y, DT.L2Expanded), oracle.pairwise_distance(x, y, DT.L2Expanded))
+    check(run(x, y, DT.CosineExpanded), oracle.pairwise_distance(x, y, DT.CosineExpanded))
+
+
 def test_golden_fixtures(golden):
     for case in ("small", "cfg1"):
         x, y = golden[f"{case}_x"], golden[f"{case}_y"]
