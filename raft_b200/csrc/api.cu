@@ -53,12 +53,15 @@ static EncodeTiledFn get_encode()
 }
 
 // packed operand [rows][nkb*64] fp16, box = 64 x box_rows, SWIZZLE_128B
-static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int nkb, int box_rows)
+static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int nkb, int box_rows,
+                            int kb0 = 0, int nkb_total = 0)
 {
+  if (nkb_total == 0) nkb_total = nkb;
+  base = static_cast<const char*>(base) + static_cast<size_t>(kb0) * 128;  // K chunk [kb0, kb0 + nkb) of every row
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[2]    = {static_cast<cuuint64_t>(nkb) * 64, static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(nkb) * 128};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(nkb_total) * 128};
   cuuint32_t box[2]     = {64, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2]    = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
@@ -181,13 +184,15 @@ static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensor
   return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, kTma>(s, ma, mb, md, p, grid);
 }
 
-static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post)
+static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post, int kb0 = 0,
+                     int nkb_chunk = 0)
 {
   int sms = 0, cc = 0;
   int rc  = device_sms(&sms, &cc);
   if (rc) return rc;
   if (cc != 10) return fail(B2D_ERR_CUDA, "raft_b200 requires an sm_100 (B200) device; found cc major " + std::to_string(cc));
-  p.nkb     = static_cast<int>((k + 31) / 32);
+  const int nkb_total = static_cast<int>((k + 31) / 32);
+  p.nkb     = nkb_chunk ? nkb_chunk : nkb_total;
   p.tiles_m = static_cast<int>((p.m + TC_BM - 1) / TC_BM);
   p.tiles_n = static_cast<int>((p.n + TC_BN - 1) / TC_BN);
   int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
@@ -204,9 +209,9 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb, md;
   memset(&md, 0, sizeof(md));
-  rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
+  rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM, kb0, nkb_total);
   if (rc) return rc;
-  rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN);
+  rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN, kb0, nkb_total);
   if (rc) return rc;
   const int grid      = static_cast<int>(p.n_items < sms ? p.n_items : sms);
   const bool resident = p.nkb <= TC_MAX_RES_KB;
@@ -217,7 +222,8 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
   // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
   // unaligned outputs take the direct register->global path
-  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0);
+  bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0) &&
+             p.acc_mode == 0;  // the K-chunked read-modify-write epilogue lives in the direct path
   if (tma) {
     rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
     if (rc) return rc;
@@ -360,6 +366,18 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd;
     p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy) ? 1 : 0;
     p.pair_ok   = (reinterpret_cast<uintptr_t>(dist) % 8 == 0 && ldd % 2 == 0) ? 1 : 0;
+    // k > 256: accumulate K in chunks of 128 columns (the resident kernel), each added to dist with a
+    // round-to-nearest fp32 add -- bounds the truncation bias of long MMA chains (numerics)
+    const int nkb_total = static_cast<int>((k + 31) / 32);
+    if (nkb_total > 8) {
+      for (int kb0 = 0; kb0 < nkb_total; kb0 += TC_MAX_RES_KB) {
+        const int nk = nkb_total - kb0 < TC_MAX_RES_KB ? nkb_total - kb0 : TC_MAX_RES_KB;
+        p.acc_mode   = kb0 == 0 ? 1 : (kb0 + nk >= nkb_total ? 3 : 2);
+        rc           = launch_tc(s, w, p, k, EPI_STORE, post, kb0, nk);
+        if (rc) return rc;
+      }
+      return B2D_OK;
+    }
     return launch_tc(s, w, p, k, EPI_STORE, post);
   }
 

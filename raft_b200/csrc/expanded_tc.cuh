@@ -75,6 +75,7 @@ struct TcParams {
   int64_t ldd;
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
   int pair_ok;            // dist 8-byte aligned and ldd even -> st.v2
+  int acc_mode;           // K-chunked accumulation: 0 single pass, 1 first chunk (raw store), 2 middle (+=), 3 last (+=, post)
   // EPI_MINLOC
   long long* keys;        // [m] packed (ordered float bits << 32 | index)
   int64_t idx_offset;
@@ -320,6 +321,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
         float tv = kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f;  // +inf: never the arg-min
         if (gj < p.n) tv = __ldg(&p.yt[gj]);
+        if (kEpi == EPI_STORE && p.acc_mode >= 2) tv = 0.f;  // the t terms entered with the first K chunk
         col_tb[et] = tv;
       }
       ptx::bar_sync(1, 32 * TC_EPI_WARPS);
@@ -418,7 +420,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           float rv = 0.f;
           thr[j]   = __int_as_float(0xff800000);  // -inf: rows outside the matrix never trigger
           if (row0 + 8 * j < p.m) {
-            if (kEpi == EPI_STORE) rv = __ldg(&p.xt[row0 + 8 * j]);
+            if (kEpi == EPI_STORE && p.acc_mode < 2) rv = __ldg(&p.xt[row0 + 8 * j]);
             if (kEpi == EPI_MINLOC) {
               const long long ck = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
               const int sb       = static_cast<int>(ck >> 32);
@@ -484,7 +486,26 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (kEpi == EPI_STORE) {
             const int64_t gi0 = row0 + 16 * rh;                 // global row of v[4i], v[4i+1]
             const int64_t gj0 = col0 + cc * 64 + 2 * tq;        // global column of v[4i]
-            if (kPost != POST_NONE) {
+            if (p.acc_mode >= 2) {
+              // K-chunked accumulation (k > 256): add this chunk's contribution to what the earlier
+              // chunks left in dist -- a round-to-nearest fp32 add per chunk instead of ever longer
+              // truncating MMA chains on one accumulator
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int64_t gj = gj0 + 8 * i;
+                const float* q0  = p.dist + gi0 * p.ldd + gj;
+                const float* q1  = q0 + 8 * p.ldd;
+                if (gi0 < p.m) {
+                  if (gj < p.n) v[4 * i] += __ldcs(q0);
+                  if (gj + 1 < p.n) v[4 * i + 1] += __ldcs(q0 + 1);
+                }
+                if (gi0 + 8 < p.m) {
+                  if (gj < p.n) v[4 * i + 2] += __ldcs(q1);
+                  if (gj + 1 < p.n) v[4 * i + 3] += __ldcs(q1 + 1);
+                }
+              }
+            }
+            if (kPost != POST_NONE && (p.acc_mode == 0 || p.acc_mode == 3)) {
 #pragma unroll
               for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
               if (p.diag_zero) {

@@ -54,13 +54,14 @@ def test_inner_product_vs_oracle():
     assert (np.abs(got - ref) <= 1e-5 * scale + 1e-6).all()
 
 
-@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.CosineExpanded, DT.L1])
-@pytest.mark.parametrize("shape", [(1024, 32, 1024), (32, 1024, 1024)])
+@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.L2SqrtExpanded, DT.CosineExpanded, DT.L1])
+@pytest.mark.parametrize("shape", [(1024, 32, 1024), (32, 1024, 1024), (300, 700, 1000), (513, 300, 300)])
 def test_reference_test_shapes_large_k(metric, shape):
-    # k = 1024: the tensor-core accumulator truncates per MMA, error grows with k;
-    # the reference's own tests used 1e-3 for these shapes
+    # k > 256: the tensor path accumulates K in chunks of 128 with an fp32 add per chunk, which keeps
+    # the 1e-4 bar (a single 1024-deep MMA chain measured 2.1e-4 on intra-cluster pairs; the
+    # reference's own tests used 1e-3 for these shapes)
     x, y = blobs(*shape)
-    check(run(x, y, metric), oracle.pairwise_distance(x, y, metric), eps=1e-3)
+    check(run(x, y, metric), oracle.pairwise_distance(x, y, metric))
 
 
 @pytest.mark.parametrize("metric", [DT.L2Expanded, DT.L2SqrtExpanded, DT.CosineExpanded, DT.L1, DT.Linf])
