@@ -366,12 +366,13 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd;
     p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy) ? 1 : 0;
     p.pair_ok   = (reinterpret_cast<uintptr_t>(dist) % 8 == 0 && ldd % 2 == 0) ? 1 : 0;
-    // k > 256: accumulate K in chunks of 128 columns (the resident kernel), each added to dist with a
-    // round-to-nearest fp32 add -- bounds the truncation bias of long MMA chains (numerics)
+    // k > 320: accumulate K in chunks of 256 columns, each added to dist with a round-to-nearest fp32
+    // add -- bounds the truncation bias of long MMA chains (numerics)
     const int nkb_total = static_cast<int>((k + 31) / 32);
-    if (nkb_total > 8) {
-      for (int kb0 = 0; kb0 < nkb_total; kb0 += TC_MAX_RES_KB) {
-        const int nk = nkb_total - kb0 < TC_MAX_RES_KB ? nkb_total - kb0 : TC_MAX_RES_KB;
+    constexpr int kChunk = 8;
+    if (nkb_total > 10) {
+      for (int kb0 = 0; kb0 < nkb_total; kb0 += kChunk) {
+        const int nk = nkb_total - kb0 < kChunk ? nkb_total - kb0 : kChunk;
         p.acc_mode   = kb0 == 0 ? 1 : (kb0 + nk >= nkb_total ? 3 : 2);
         rc           = launch_tc(s, w, p, k, EPI_STORE, post, kb0, nk);
         if (rc) return rc;

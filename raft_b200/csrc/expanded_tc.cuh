@@ -490,18 +490,34 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               // K-chunked accumulation (k > 256): add this chunk's contribution to what the earlier
               // chunks left in dist -- a round-to-nearest fp32 add per chunk instead of ever longer
               // truncating MMA chains on one accumulator
+              if (rows_in && cols_in && p.pair_ok) {
+                const float* q0 = p.dist + gi0 * p.ldd + gj0;
+                const float* q1 = q0 + 8 * p.ldd;
+                float2 o0[8], o1[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int64_t gj = gj0 + 8 * i;
-                const float* q0  = p.dist + gi0 * p.ldd + gj;
-                const float* q1  = q0 + 8 * p.ldd;
-                if (gi0 < p.m) {
-                  if (gj < p.n) v[4 * i] += __ldcs(q0);
-                  if (gj + 1 < p.n) v[4 * i + 1] += __ldcs(q0 + 1);
+                for (int i = 0; i < 8; ++i) {
+                  o0[i] = __ldcs(reinterpret_cast<const float2*>(q0 + 8 * i));
+                  o1[i] = __ldcs(reinterpret_cast<const float2*>(q1 + 8 * i));
                 }
-                if (gi0 + 8 < p.m) {
-                  if (gj < p.n) v[4 * i + 2] += __ldcs(q1);
-                  if (gj + 1 < p.n) v[4 * i + 3] += __ldcs(q1 + 1);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  v[4 * i] += o0[i].x; v[4 * i + 1] += o0[i].y;
+                  v[4 * i + 2] += o1[i].x; v[4 * i + 3] += o1[i].y;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int64_t gj = gj0 + 8 * i;
+                  const float* q0  = p.dist + gi0 * p.ldd + gj;
+                  const float* q1  = q0 + 8 * p.ldd;
+                  if (gi0 < p.m) {
+                    if (gj < p.n) v[4 * i] += __ldcs(q0);
+                    if (gj + 1 < p.n) v[4 * i + 1] += __ldcs(q0 + 1);
+                  }
+                  if (gi0 + 8 < p.m) {
+                    if (gj < p.n) v[4 * i + 2] += __ldcs(q1);
+                    if (gj + 1 < p.n) v[4 * i + 3] += __ldcs(q1 + 1);
+                  }
                 }
               }
             }
