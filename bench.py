@@ -232,7 +232,42 @@ def run_pairwise_1gpu(args):
             "kernel": "expanded_tc_kernel (tcgen05, EPI_STORE) incl. the two operand-prep launches (<2% of the step)",
             "traffic": ncu_traffic("pairwise_100k")}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    # quick parity spot check of the timed result against the oracle (never on the timed path)
+    # ---- the other BASELINE.json configs, timed briefly in the same run (parity for them lives in tests/)
+    others = {}
+
+    def t_ms(f, steps=3, warm=1):
+        ms_, _ = time_steps(f, steps, warm, torch)
+        return ms_
+    for metric in ("cosine", "correlation"):
+        ms_o = t_ms(lambda: pairwise_distance(x, y, out=out, metric=metric, handle=h))
+        others[f"{metric} 100000x100000x128 f32"] = {"ms": ms_o, "pairs_per_s": pairs / (ms_o * 1e-3),
+                                                     "hbm_gbs": alg_bytes / (ms_o * 1e-3) / 1e9}
+    m3, k3 = 50_000, 256
+    c3 = centers_device(k3, torch, dev)
+    x3 = blobs_device(m3, k3, 1234, c3, torch, dev)
+    y3 = blobs_device(m3, k3, 4321, c3, torch, dev)
+    out3 = out.view(-1)[: m3 * m3].view(m3, m3)
+    for metric, name in (("cityblock", "L1"), ("sqeuclidean_unexpanded", "L2Unexpanded"), ("chebyshev", "Linf")):
+        ms_o = t_ms(lambda: pairwise_distance(x3, y3, out=out3, metric=metric, handle=h), steps=2)
+        others[f"{name} 50000x50000x256 f32"] = {
+            "ms": ms_o, "pairs_per_s": m3 * m3 / (ms_o * 1e-3),
+            "hbm_gbs": (8.0 * m3 * k3 + 4.0 * m3 * m3) / (ms_o * 1e-3) / 1e9,
+            "fp32_lane_ops_per_s": 2.0 * m3 * m3 * k3 / (ms_o * 1e-3), "bound": "fp32 pipe (148 SMs x 128 lanes x clk)"}
+    del x3, y3
+    # fp16-in / fp32-accumulate 200000x200000x64: the 160 GB result is produced in 4 row blocks into a reused buffer
+    m5, k5, blk = 200_000, 64, 50_000
+    c5 = centers_device(k5, torch, dev)
+    x5 = blobs_device(m5, k5, 1234, c5, torch, dev).half()
+    y5 = blobs_device(m5, k5, 4321, c5, torch, dev).half()
+    out5 = out.view(-1)[: blk * m5].view(blk, m5)
+
+    def fp16_pass():
+        for r0 in range(0, m5, blk):
+            pairwise_distance(x5[r0:r0 + blk], y5, out=out5, metric="sqeuclidean", handle=h)
+    ms_o = t_ms(fp16_pass, steps=2)
+    others["L2Expanded 200000x200000x64 f16-in/f32-acc (4 row blocks, reused 40 GB buffer)"] = {
+        "ms": ms_o, "pairs_per_s": float(m5) * m5 / (ms_o * 1e-3), "hbm_gbs": 4.0 * m5 * m5 / (ms_o * 1e-3) / 1e9}
+    del x5, y5, out5, out3
     del out
     torch.cuda.empty_cache()
 
@@ -278,7 +313,7 @@ def run_pairwise_1gpu(args):
                        "precision": "fp32-grade: 3-term fp16 hi/lo split, fp32 accumulate in TMEM",
                        "l2": "every step streams 40 GB of output through the 126 MB L2 (no reuse across steps)"},
             "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 3 * args.steps,
-            "clocks": clocks, "fused_l2_nn": nn, "ms_per_step_all": [round(v, 4) for v in per]}
+            "clocks": clocks, "fused_l2_nn": nn, "other_configs": others, "ms_per_step_all": [round(v, 4) for v in per]}
     print(json.dumps(line))
 
 

@@ -90,6 +90,7 @@ struct TcWorkspace {
   long long* keys;
   unsigned* gmax;  // [2]
   float* coef;     // [1]
+  unsigned* has_lo;  // [1]
   size_t bytes;
 };
 
@@ -108,6 +109,7 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   // (b2d_fused_l2_nn_finalize finds |x_i|^2 again without knowing n or k)
   w.gmax = reinterpret_cast<unsigned*>(c + take(16));
   w.coef = reinterpret_cast<float*>(w.gmax + 2);
+  w.has_lo = w.gmax + 3;
   w.xt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4));
   w.keys = reinterpret_cast<long long*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
   w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
@@ -137,7 +139,7 @@ static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int6
   p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, xn};
   p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, yn};
   p.k = static_cast<int>(k); p.nkb = static_cast<int>((k + 31) / 32); p.mode = mode; p.center = center;
-  p.gmax = w.gmax; p.coef = w.coef;
+  p.gmax = w.gmax; p.coef = w.coef; p.has_lo = w.has_lo;
   B2D_CUDA(cudaMemsetAsync(w.gmax, 0, 16, s));
   const int64_t blocks = (m + n + 7) / 8;
   prep_max_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
@@ -206,6 +208,7 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.xt       = w.xt;
   p.yt       = w.yt;
   p.coef     = w.coef;
+  p.has_lo   = w.has_lo;
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb, md;
   memset(&md, 0, sizeof(md));

@@ -70,6 +70,7 @@ struct TcParams {
   const float* xt;        // [m] row term t_x[i]
   const float* yt;        // [n] column term t_y[j]
   const float* coef;      // [1] scalar c: d = acc * c + (t_x[i] + t_y[j])  (prep.cuh)
+  const unsigned* has_lo; // [1] 0: every operand is exact in fp16 -> the cross-term MMAs are skipped
   // EPI_STORE
   float* dist;
   int64_t ldd;
@@ -220,6 +221,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // descriptor start-address units are 16 B; inside the 128-B swizzled row of a k-block:
     //   hi k[0,16) +0, hi k[16,32) +2, lo k[0,16) +4, lo k[16,32) +6
     uint32_t a_it = 0, t_it = 0, it_local = 0;
+    const bool has_lo = __ldg(p.has_lo) != 0u;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
       const int ch  = static_cast<int>(item / p.tiles_n);
       const int mt0 = ch * p.chunk;
@@ -237,7 +239,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (mt == mt0) ptx::mbar_wait(&bfull[kb], it_local & 1);
             ptx::mbar_wait(&afull[s], ph);
             ptx::tc_fence_after();
-            if (ptx::elect_one()) {
+            if (has_lo && ptx::elect_one()) {
               const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(a_base + s * TC_A_BYTES));
               const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(b_base + kb * TC_B_BYTES));
               ptx::mma_f16_ss(d, da + 4, db + 0, idesc, kb > 0 ? 1u : 0u);  // lo0 * hi0
@@ -253,8 +255,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (ptx::elect_one()) {
               const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(a_base + s * TC_A_BYTES));
               const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(b_base + kb * TC_B_BYTES));
-              ptx::mma_f16_ss(d, da + 0, db + 0, idesc, 1u);  // hi0 * hi0
-              ptx::mma_f16_ss(d, da + 2, db + 2, idesc, 1u);  // hi1 * hi1
+              ptx::mma_f16_ss(d, da + 0, db + 0, idesc, (has_lo || kb > 0) ? 1u : 0u);  // hi0 * hi0
+              ptx::mma_f16_ss(d, da + 2, db + 2, idesc, 1u);                           // hi1 * hi1
               ptx::mma_commit(&aempty[s]);
               if (mt == mt1 - 1) ptx::mma_commit(&bempty[kb]);
             }
@@ -280,10 +282,12 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               for (int h = 0; h < 2; ++h) {
                 const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(b_base + s * TC_B_BYTES + h * (TC_B_BYTES / 2)));
                 const uint32_t d  = tmem_base + h * 256;  // main at +0, cross at +128
-                ptx::mma_f16_ss(d + 128, da + 4, db + 0, idesc, acc);
-                ptx::mma_f16_ss(d + 128, da + 6, db + 2, idesc, 1u);
-                ptx::mma_f16_ss(d + 128, da + 0, db + 4, idesc, 1u);
-                ptx::mma_f16_ss(d + 128, da + 2, db + 6, idesc, 1u);
+                if (has_lo) {
+                  ptx::mma_f16_ss(d + 128, da + 4, db + 0, idesc, acc);
+                  ptx::mma_f16_ss(d + 128, da + 6, db + 2, idesc, 1u);
+                  ptx::mma_f16_ss(d + 128, da + 0, db + 4, idesc, 1u);
+                  ptx::mma_f16_ss(d + 128, da + 2, db + 6, idesc, 1u);
+                }
                 ptx::mma_f16_ss(d, da + 0, db + 0, idesc, acc);
                 ptx::mma_f16_ss(d, da + 2, db + 2, idesc, 1u);
               }
@@ -308,6 +312,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int tq   = lane & 3;          // fragment column pair inside an 8-column group
     uint32_t t_it  = 0;
     const float cf     = __ldg(p.coef);
+    const bool add_cross = !kResident && __ldg(p.has_lo) != 0u;  // streaming layout keeps cross terms apart
     const uint64_t pol_st = ptx::policy_evict_first();
     const uint64_t cf2 = pk(cf, cf);
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -364,7 +369,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int c = 0; c < 32; c += 4) {
               const float4 tb = *reinterpret_cast<const float4*>(&col_tb[cbase + c]);
               uint64_t a0 = pk(r[c], r[c + 1]), a1 = pk(r[c + 2], r[c + 3]);
-              if (!kResident) {
+              if (add_cross) {
                 a0 = add2(a0, pk(rc[c], rc[c + 1]));
                 a1 = add2(a1, pk(rc[c + 2], rc[c + 3]));
               }
@@ -461,7 +466,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int i = 0; i < 8; ++i) {
             const float2 tb = *reinterpret_cast<const float2*>(&col_tb[cl0 + 8 * i]);
             uint64_t a0 = pk(r[4 * i], r[4 * i + 1]), a1 = pk(r[4 * i + 2], r[4 * i + 3]);
-            if (!kResident) {
+            if (add_cross) {
               a0 = add2(a0, pk(rc[4 * i], rc[4 * i + 1]));
               a1 = add2(a1, pk(rc[4 * i + 2], rc[4 * i + 3]));
             }

@@ -47,6 +47,7 @@ struct PrepParams {
   int center;        // subtract the row mean first (correlation)
   unsigned* gmax;    // [2] float bits of the per-matrix maximum (zeroed before prep_max_kernel)
   float* coef;       // [1] the epilogue scalar c
+  unsigned* has_lo;  // [1] set to 1 when any lo half is non-zero (zeroed before the kernels run)
 };
 
 template <typename T>
@@ -144,15 +145,21 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
 
   __half* orow   = sd.op + r * static_cast<int64_t>(p.nkb) * 64;
   const int kpad = p.nkb * 32;
+  bool any_lo    = false;
   for (int t = lane; t < kpad; t += 32) {
     float xs = 0.f;
     if (t < p.k) xs = (ld_as_float(row + t * sd.cs) - mean) * scale;
     const __half h = __float2half_rn(xs);
     const __half l = __float2half_rn(xs - __half2float(h));
+    any_lo |= (__half2float(l) != 0.f);
     const int b = t >> 5, j = t & 31;
     orow[b * 64 + j]      = h;
     orow[b * 64 + 32 + j] = l;
   }
+  // operands that are exact in fp16 (fp16 inputs, small integers, ...) need no cross terms: the MMA
+  // kernel then runs one product instead of three
+  if (__any_sync(0xffffffffu, any_lo) && lane == 0 && *reinterpret_cast<volatile unsigned*>(p.has_lo) == 0u)
+    atomicExch(p.has_lo, 1u);
   if (lane == 0) {
     float t;
     if (p.mode == PREP_L2) t = sd.ext_norm_sq ? sd.ext_norm_sq[r] : static_cast<float>(ss);

@@ -186,6 +186,24 @@ def test_fp16_inputs_tolerance_study():
     assert np.quantile(rel, 0.999) < 2e-2
 
 
+def test_fp16_exact_operands_skip_cross_terms_and_stay_exact():
+    # operands that are exact in fp16 (here: small integers in fp32 storage) take the 1-product
+    # path; the result must be the exact integer distance
+    rng = np.random.default_rng(2)
+    x = rng.integers(-8, 9, (300, 96)).astype(np.float32)
+    y = rng.integers(-8, 9, (520, 96)).astype(np.float32)
+    got = run(x, y, DT.L2Expanded)
+    ref = oracle.pairwise_distance(x, y, DT.L2Expanded)
+    assert np.array_equal(got.astype(np.float64), ref)
+    got = run(x[:, :32].copy(), y[:, :32].copy(), DT.InnerProduct)
+    assert np.array_equal(got.astype(np.float64), oracle.pairwise_distance(x[:, :32], y[:, :32], DT.InnerProduct))
+    x = rng.integers(-8, 9, (130, 400)).astype(np.float32)   # streaming layout (k > 128), chunked (k > 320)
+    y = rng.integers(-8, 9, (260, 400)).astype(np.float32)
+    assert np.array_equal(run(x, y, DT.L2Expanded).astype(np.float64), oracle.pairwise_distance(x, y, DT.L2Expanded))
+    assert np.array_equal(run(x[:, :200].copy(), y[:, :200].copy(), DT.L2Expanded).astype(np.float64),
+                          oracle.pairwise_distance(x[:, :200], y[:, :200], DT.L2Expanded))
+
+
 def test_output_conversion_and_handle():
     x, y = blobs(64, 48, 16)
     h = DeviceResources()
