@@ -60,7 +60,12 @@ enum {
   B2D_Linf                = 7,
   B2D_Canberra            = 8,
   B2D_LpUnexpanded        = 9,
-  B2D_CorrelationExpanded = 10
+  B2D_CorrelationExpanded = 10,
+  B2D_HellingerExpanded   = 12,
+  B2D_JensenShannon       = 15,
+  B2D_HammingUnexpanded   = 16,
+  B2D_KLDivergence        = 17,
+  B2D_RusselRaoExpanded   = 18
 };
 
 /* element types of x / y (dist is always fp32) */
@@ -99,6 +104,13 @@ size_t b2d_fused_l2_nn_workspace_bytes(int64_t m, int64_t n, int64_t k);
 int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, const float* y,
                     int64_t ldy, const float* xn, const float* yn, int64_t m, int64_t n, int64_t k,
                     int do_sqrt, int init_out, void* workspace, size_t workspace_bytes);
+
+/* raft::distance::fusedDistanceNN[MinReduce]: the same fused arg-min for
+ * metric in {L2Expanded, L2SqrtExpanded, CosineExpanded, CorrelationExpanded}; out[i].value is the
+ * distance in that metric.  xn / yn (optional) are squared L2 row norms and are used by the L2 metrics. */
+int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float* x, int64_t ldx,
+                          const float* y, int64_t ldy, const float* xn, const float* yn, int64_t m,
+                          int64_t n, int64_t k, int init_out, void* workspace, size_t workspace_bytes);
 
 /* Multi-GPU building blocks.  keys[i] = (order-preserving bits of (|y_j|^2 - 2 x_i.y_j) << 32)
  * | (j + idx_offset), reduced with signed 64-bit MIN: over this GPU's y shard here, then across

@@ -18,7 +18,8 @@
 /* enum raft::distance::DistanceType, SURVEY.md 8(a1) */
 enum { L2Expanded = 0, L2SqrtExpanded = 1, CosineExpanded = 2, L1 = 3, L2Unexpanded = 4,
        L2SqrtUnexpanded = 5, InnerProduct = 6, Linf = 7, Canberra = 8, LpUnexpanded = 9,
-       CorrelationExpanded = 10 };
+       CorrelationExpanded = 10, HellingerExpanded = 12, JensenShannon = 15, HammingUnexpanded = 16,
+       KLDivergence = 17, RusselRaoExpanded = 18 };
 
 static double pair_metric(const float* a, const float* b, int64_t k, int metric, double p)
 {
@@ -64,6 +65,29 @@ static double pair_metric(const float* a, const float* b, int64_t k, int metric,
     case LpUnexpanded:
       for (int64_t i = 0; i < k; ++i) acc += pow(fabs((double)a[i] - (double)b[i]), p);
       return pow(acc, 1.0 / p);
+    /* SURVEY.md 8(f) item 4 metrics ([RECALLED] definitions, see oracle.py) */
+    case HellingerExpanded:
+      for (int64_t i = 0; i < k; ++i) acc += sqrt((double)a[i]) * sqrt((double)b[i]);
+      acc = 1.0 - acc;
+      return sqrt(acc > 0.0 ? acc : 0.0);
+    case RusselRaoExpanded:
+      for (int64_t i = 0; i < k; ++i) acc += (double)a[i] * (double)b[i];
+      return ((double)k - acc) / (double)k;
+    case HammingUnexpanded:
+      for (int64_t i = 0; i < k; ++i) acc += (a[i] != b[i]) ? 1.0 : 0.0;
+      return acc / (double)k;
+    case KLDivergence:
+      for (int64_t i = 0; i < k; ++i)
+        if (a[i] != 0.f) acc += (double)a[i] * (log((double)a[i]) - log((double)b[i]));
+      return 0.5 * acc;
+    case JensenShannon:
+      for (int64_t i = 0; i < k; ++i) {
+        double mm = 0.5 * ((double)a[i] + (double)b[i]);
+        if (a[i] != 0.f) acc += (double)a[i] * (log((double)a[i]) - log(mm));
+        if (b[i] != 0.f) acc += (double)b[i] * (log((double)b[i]) - log(mm));
+      }
+      acc *= 0.5;
+      return sqrt(acc > 0.0 ? acc : 0.0);
     default: return NAN;
   }
 }

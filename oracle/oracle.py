@@ -43,9 +43,11 @@ class DistanceType(enum.IntEnum):
 
 
 EXPANDED = (DistanceType.L2Expanded, DistanceType.L2SqrtExpanded, DistanceType.CosineExpanded,
-            DistanceType.CorrelationExpanded, DistanceType.InnerProduct)
+            DistanceType.CorrelationExpanded, DistanceType.InnerProduct, DistanceType.HellingerExpanded,
+            DistanceType.RusselRaoExpanded)
 UNEXPANDED = (DistanceType.L1, DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded,
-              DistanceType.Linf, DistanceType.Canberra, DistanceType.LpUnexpanded)
+              DistanceType.Linf, DistanceType.Canberra, DistanceType.LpUnexpanded,
+              DistanceType.HammingUnexpanded, DistanceType.KLDivergence, DistanceType.JensenShannon)
 
 
 def row_norm_sq(x: np.ndarray) -> np.ndarray:
@@ -85,6 +87,27 @@ def _block(x64, y64, metric, p):
         yn = np.sqrt(np.einsum("ij,ij->i", yc, yc))
         with np.errstate(divide="ignore", invalid="ignore"):
             return 1.0 - (xc @ yc.T) / (xn[:, None] * yn[None, :])
+    # SURVEY.md 8(f) item 4 metrics.  [RECALLED] definitions of the removed reference ops:
+    #   Hellinger  sqrt(max(0, 1 - sum sqrt(x_i) sqrt(y_i)))        RusselRao  (k - sum x_i y_i) / k
+    #   Hamming    (# x_i != y_i) / k                               JensenShannon  sqrt(0.5 sum x log(x/m) + y log(y/m))
+    #   KLDivergence  0.5 * sum x_i log(x_i / y_i)  (the 0.5 is the reference's epilogue, not scipy's)
+    if metric == DistanceType.HellingerExpanded:
+        return np.sqrt(np.maximum(1.0 - np.sqrt(x64) @ np.sqrt(y64).T, 0.0))
+    if metric == DistanceType.RusselRaoExpanded:
+        k = x64.shape[1]
+        return (k - x64 @ y64.T) / k
+    if metric == DistanceType.HammingUnexpanded:
+        return (x64[:, None, :] != y64[None, :, :]).mean(axis=2)
+    if metric in (DistanceType.KLDivergence, DistanceType.JensenShannon):
+        a, b = x64[:, None, :], y64[None, :, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if metric == DistanceType.KLDivergence:
+                t = np.where(a == 0.0, 0.0, a * (np.log(a) - np.log(b)))
+                return 0.5 * t.sum(axis=2)
+            mm = 0.5 * (a + b)
+            ta = np.where(a == 0.0, 0.0, a * (np.log(a) - np.log(mm)))
+            tb = np.where(b == 0.0, 0.0, b * (np.log(b) - np.log(mm)))
+            return np.sqrt(np.maximum(0.5 * (ta + tb).sum(axis=2), 0.0))
     # unexpanded metrics: SURVEY.md 8(a4)
     diff = x64[:, None, :] - y64[None, :, :]
     if metric == DistanceType.L1:
@@ -116,6 +139,8 @@ def pairwise_distance(x, y, metric=DistanceType.L2Expanded, metric_arg: float = 
     out = np.empty((m, n), dtype=np.float64)
     if metric in EXPANDED + (DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded):
         block = max(block, 2048)
+    elif metric in (DistanceType.KLDivergence, DistanceType.JensenShannon, DistanceType.HammingUnexpanded):
+        block = min(block, 128)
     for i0 in range(0, m, block):
         for j0 in range(0, n, block):
             out[i0:i0 + block, j0:j0 + block] = _block(

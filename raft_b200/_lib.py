@@ -11,7 +11,7 @@ _lib = None
 # every symbol include/raft_b200.h declares
 SYMBOLS = [
     "b2d_version", "b2d_last_error", "b2d_pairwise_workspace_bytes", "b2d_pairwise_distance",
-    "b2d_fused_l2_nn_workspace_bytes", "b2d_fused_l2_nn", "b2d_fused_l2_nn_keys",
+    "b2d_fused_l2_nn_workspace_bytes", "b2d_fused_l2_nn", "b2d_fused_distance_nn", "b2d_fused_l2_nn_keys",
     "b2d_fused_l2_nn_finalize", "b2d_row_norm",
 ]
 
@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
     L.b2d_fused_l2_nn_workspace_bytes.argtypes = [i64, i64, i64]
     L.b2d_fused_l2_nn.restype = ci
     L.b2d_fused_l2_nn.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, i64, i64, i64, ci, ci, vp, sz]
+    L.b2d_fused_distance_nn.restype = ci
+    L.b2d_fused_distance_nn.argtypes = [vp, vp, ci, vp, i64, vp, i64, vp, vp, i64, i64, i64, ci, vp, sz]
     L.b2d_fused_l2_nn_keys.restype = ci
     L.b2d_fused_l2_nn_keys.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, i64, i64, i64, i64, ci, vp, sz]
     L.b2d_fused_l2_nn_finalize.restype = ci

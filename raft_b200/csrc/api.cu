@@ -122,24 +122,27 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
 static bool is_expanded(int metric)
 {
   return metric == B2D_L2Expanded || metric == B2D_L2SqrtExpanded || metric == B2D_CosineExpanded ||
-         metric == B2D_CorrelationExpanded || metric == B2D_InnerProduct;
+         metric == B2D_CorrelationExpanded || metric == B2D_InnerProduct || metric == B2D_HellingerExpanded ||
+         metric == B2D_RusselRaoExpanded;
 }
 static bool is_unexpanded(int metric)
 {
   return metric == B2D_L1 || metric == B2D_L2Unexpanded || metric == B2D_L2SqrtUnexpanded ||
-         metric == B2D_Linf || metric == B2D_Canberra || metric == B2D_LpUnexpanded;
+         metric == B2D_Linf || metric == B2D_Canberra || metric == B2D_LpUnexpanded ||
+         metric == B2D_HammingUnexpanded || metric == B2D_KLDivergence || metric == B2D_JensenShannon;
 }
 
 template <typename T>
 static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int64_t xrs, int64_t xcs, int64_t m,
                        const void* y, int64_t yrs, int64_t ycs, int64_t n, int64_t k, const float* xn, const float* yn,
-                       int mode, int center)
+                       int mode, int center, int xform = 0, float coef_mul = 1.f, float tx_const = 0.f)
 {
   PrepParams p;
   p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, xn};
   p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, yn};
   p.k = static_cast<int>(k); p.nkb = static_cast<int>((k + 31) / 32); p.mode = mode; p.center = center;
   p.gmax = w.gmax; p.coef = w.coef; p.has_lo = w.has_lo;
+  p.xform = xform; p.coef_mul = coef_mul; p.tx_const = tx_const;
   B2D_CUDA(cudaMemsetAsync(w.gmax, 0, 16, s));
   const int64_t blocks = (m + n + 7) / 8;
   prep_max_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
@@ -354,20 +357,25 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
       return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
     TcWorkspace w = tc_layout(workspace, ma, na, k, false);
-    int mode = PREP_L2, center = 0, post = POST_NONE;
+    int mode = PREP_L2, center = 0, post = POST_NONE, xform = 0;
+    float coef_mul = 1.f, tx_const = 0.f;
     if (metric == B2D_L2Expanded) { post = POST_CLAMP; }
     else if (metric == B2D_L2SqrtExpanded) { post = POST_CLAMP_SQRT; }
     else if (metric == B2D_CosineExpanded) { mode = PREP_COSINE; }
     else if (metric == B2D_CorrelationExpanded) { mode = PREP_COSINE; center = 1; }
+    else if (metric == B2D_HellingerExpanded) { mode = PREP_INNER; post = POST_CLAMP_SQRT; xform = 1; coef_mul = -1.f; tx_const = 1.f; }
+    else if (metric == B2D_RusselRaoExpanded) { mode = PREP_INNER; coef_mul = -1.f / static_cast<float>(k); tx_const = 1.f; }
     else { mode = PREP_INNER; }
     int rc = dtype == B2D_F32
-               ? launch_prep<float>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center)
-               : launch_prep<__half>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center);
+               ? launch_prep<float>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center, xform,
+                                    coef_mul, tx_const)
+               : launch_prep<__half>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center, xform,
+                                     coef_mul, tx_const);
     if (rc) return rc;
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.m = ma; p.n = na; p.dist = dist; p.ldd = ldd;
-    p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy) ? 1 : 0;
+    p.diag_zero = (post != POST_NONE && x == y && m == n && ldx == ldy && mode == PREP_L2) ? 1 : 0;
     p.pair_ok   = (reinterpret_cast<uintptr_t>(dist) % 8 == 0 && ldd % 2 == 0) ? 1 : 0;
     // k > 320: accumulate K in chunks of 256 columns, each added to dist with a round-to-nearest fp32
     // add -- bounds the truncation bias of long MMA chains (numerics)
@@ -392,7 +400,7 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
   p.xrs = xrs; p.xcs = xcs; p.yrs = yrs; p.ycs = ycs; p.ldd = ldd; p.m = ma; p.n = na; p.k = static_cast<int>(k);
   p.vec_x = (xcs == 1 && xrs % 4 == 0 && k % 4 == 0 && reinterpret_cast<uintptr_t>(xa) % 16 == 0) ? 1 : 0;
   p.vec_y = (ycs == 1 && yrs % 4 == 0 && k % 4 == 0 && reinterpret_cast<uintptr_t>(ya) % 16 == 0) ? 1 : 0;
-  p.p = metric_arg; p.inv_p = 1.f / metric_arg;
+  p.p = metric_arg; p.inv_p = metric == B2D_HammingUnexpanded ? 1.f / static_cast<float>(k) : 1.f / metric_arg;
   p.tiles_n = static_cast<int>((na + UX_BN - 1) / UX_BN);
   const int64_t tiles = ((ma + UX_BM - 1) / UX_BM) * p.tiles_n;
   int cc = 0, sms = 0;
@@ -405,6 +413,9 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     case B2D_L2SqrtUnexpanded: return launch_ux_inst<UX_L2SQRT>(s, p, tiles);
     case B2D_Linf: return launch_ux_inst<UX_LINF>(s, p, tiles);
     case B2D_Canberra: return launch_ux_inst<UX_CANBERRA>(s, p, tiles);
+    case B2D_HammingUnexpanded: return launch_ux_inst<UX_HAMMING>(s, p, tiles);
+    case B2D_KLDivergence: return launch_ux_inst<UX_KL>(s, p, tiles);
+    case B2D_JensenShannon: return launch_ux_inst<UX_JS>(s, p, tiles);
     default: return launch_ux_inst<UX_LP>(s, p, tiles);
   }
 }
@@ -415,9 +426,9 @@ size_t b2d_fused_l2_nn_workspace_bytes(int64_t m, int64_t n, int64_t k)
   return tc_layout(nullptr, m, n, k, true).bytes;
 }
 
-int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
+static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
                          const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int64_t idx_offset,
-                         int init_keys, void* workspace, size_t workspace_bytes)
+                         int init_keys, void* workspace, size_t workspace_bytes, int mode, int center)
 {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
@@ -434,13 +445,21 @@ int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
     minloc_init_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), m);
     B2D_CUDA(cudaGetLastError());
   }
-  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, PREP_L2, 0);
+  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, mode, center);
   if (rc) return rc;
   if (n == 0) return B2D_OK;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
   return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+}
+
+int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                         const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int64_t idx_offset,
+                         int init_keys, void* workspace, size_t workspace_bytes)
+{
+  return fused_nn_keys(stream, keys, x, ldx, y, ldy, xn, yn, m, n, k, idx_offset, init_keys, workspace,
+                       workspace_bytes, PREP_L2, 0);
 }
 
 int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys, int64_t m, int do_sqrt,
@@ -475,6 +494,33 @@ int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, 
   if (rc) return rc;
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
     reinterpret_cast<KvpIF*>(out), w.keys, w.xt, m, do_sqrt, init_out ? 0 : 1);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float* x, int64_t ldx, const float* y,
+                          int64_t ldy, const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int init_out,
+                          void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (metric == B2D_L2Expanded || metric == B2D_L2SqrtExpanded)
+    return b2d_fused_l2_nn(stream, out, x, ldx, y, ldy, xn, yn, m, n, k, metric == B2D_L2SqrtExpanded ? 1 : 0, init_out,
+                           workspace, workspace_bytes);
+  if (metric != B2D_CosineExpanded && metric != B2D_CorrelationExpanded)
+    return fail(B2D_ERR_UNSUPPORTED, "fusedDistanceNN supports L2Expanded, L2SqrtExpanded, CosineExpanded, CorrelationExpanded");
+  if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
+  if (m == 0) return B2D_OK;
+  if (!out) return fail(B2D_ERR_INVALID_ARG, "null out");
+  const size_t need = tc_layout(nullptr, m, n, k, true).bytes;
+  if (!workspace || workspace_bytes < need)
+    return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  TcWorkspace w = tc_layout(workspace, m, n, k, true);
+  // cosine family: rows are normalised in prep, keys hold -cos, the row term t_x = 1 turns it into 1 - cos
+  int rc = fused_nn_keys(stream, reinterpret_cast<int64_t*>(w.keys), x, ldx, y, ldy, nullptr, nullptr, m, n, k, 0, 1,
+                         workspace, workspace_bytes, PREP_COSINE, metric == B2D_CorrelationExpanded ? 1 : 0);
+  if (rc) return rc;
+  minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
+    reinterpret_cast<KvpIF*>(out), w.keys, w.xt, m, 0, init_out ? 0 : 1);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }

@@ -45,6 +45,9 @@ struct PrepParams {
   int k, nkb;
   int mode;          // PrepMode
   int center;        // subtract the row mean first (correlation)
+  int xform;         // 1: take sqrt of every element first (HellingerExpanded)
+  float coef_mul;    // extra factor on the epilogue scalar (RusselRao: -1/k, Hellinger: -1)
+  float tx_const;    // PREP_INNER: row term of x (Hellinger / RusselRao: 1 -> d = 1 - ...)
   unsigned* gmax;    // [2] float bits of the per-matrix maximum (zeroed before prep_max_kernel)
   float* coef;       // [1] the epilogue scalar c
   unsigned* has_lo;  // [1] set to 1 when any lo half is non-zero (zeroed before the kernels run)
@@ -56,6 +59,12 @@ template <>
 __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
 template <>
 __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <typename T>
+__device__ __forceinline__ float ld_elem(const T* p, int xform)
+{
+  const float v = ld_as_float(p);
+  return xform ? sqrtf(v) : v;
+}
 
 __device__ __forceinline__ int scale_exponent(float amax)
 {
@@ -71,13 +80,13 @@ __device__ __forceinline__ int scale_exponent(float amax)
 
 // mean (if centring) and sum of squares of a row, warp-cooperative
 template <typename T>
-__device__ __forceinline__ void row_stats(const T* row, int64_t cs, int k, int center, int lane, float& mean,
-                                          double& ss, float& amax)
+__device__ __forceinline__ void row_stats(const T* row, int64_t cs, int k, int center, int xform, int lane,
+                                          float& mean, double& ss, float& amax)
 {
   mean = 0.f;
   if (center) {
     double s = 0.0;
-    for (int t = lane; t < k; t += 32) s += static_cast<double>(ld_as_float(row + t * cs));
+    for (int t = lane; t < k; t += 32) s += static_cast<double>(ld_elem(row + t * cs, xform));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     mean = static_cast<float>(s / static_cast<double>(k));
@@ -85,7 +94,7 @@ __device__ __forceinline__ void row_stats(const T* row, int64_t cs, int k, int c
   amax = 0.f;
   ss   = 0.0;
   for (int t = lane; t < k; t += 32) {
-    const float v = ld_as_float(row + t * cs) - mean;
+    const float v = ld_elem(row + t * cs, xform) - mean;
     amax          = fmaxf(amax, fabsf(v));
     ss += static_cast<double>(v) * static_cast<double>(v);
   }
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(256) prep_max_kernel(PrepParams p)
   const T* row = static_cast<const T*>(sd.src) + r * sd.rs;
   float mean, amax;
   double ss;
-  row_stats(row, sd.cs, p.k, p.center, lane, mean, ss, amax);
+  row_stats(row, sd.cs, p.k, p.center, p.xform, lane, mean, ss, amax);
   if (p.mode == PREP_COSINE) amax = ss > 0.0 ? static_cast<float>(static_cast<double>(amax) / sqrt(ss)) : 0.f;
   // atomics only when the value can raise the maximum (200k same-address atomics cost ~140 us;
   // with the read-first test they become O(log rows))
@@ -132,11 +141,11 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   const int ey = scale_exponent(__uint_as_float(p.gmax[1]));
   if (which == 0 && r == 0 && lane == 0) {
     const float c = p.mode == PREP_L2 ? -2.f : (p.mode == PREP_COSINE ? -1.f : 1.f);
-    *p.coef       = c * ldexpf(1.f, -ex) * ldexpf(1.f, -ey);
+    *p.coef       = c * p.coef_mul * ldexpf(1.f, -ex) * ldexpf(1.f, -ey);
   }
   float mean, amax;
   double ss;
-  row_stats(row, sd.cs, p.k, p.center, lane, mean, ss, amax);
+  row_stats(row, sd.cs, p.k, p.center, p.xform, lane, mean, ss, amax);
   float scale = ldexpf(1.f, which ? ey : ex);
   if (p.mode == PREP_COSINE) {
     const double nrm = sd.ext_norm_sq ? sqrt(static_cast<double>(sd.ext_norm_sq[r])) : sqrt(ss);
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   bool any_lo    = false;
   for (int t = lane; t < kpad; t += 32) {
     float xs = 0.f;
-    if (t < p.k) xs = (ld_as_float(row + t * sd.cs) - mean) * scale;
+    if (t < p.k) xs = (ld_elem(row + t * sd.cs, p.xform) - mean) * scale;
     const __half h = __float2half_rn(xs);
     const __half l = __float2half_rn(xs - __half2float(h));
     any_lo |= (__half2float(l) != 0.f);
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
     float t;
     if (p.mode == PREP_L2) t = sd.ext_norm_sq ? sd.ext_norm_sq[r] : static_cast<float>(ss);
     else if (p.mode == PREP_COSINE) t = which == 0 ? 1.f : 0.f;
-    else t = 0.f;
+    else t = which == 0 ? p.tx_const : 0.f;
     sd.tvec[r] = t;
   }
 }

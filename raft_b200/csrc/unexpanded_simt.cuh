@@ -23,7 +23,8 @@ constexpr int UX_SMEM_BYTES = 2 * (UX_BM + UX_BN) * UX_KB * 4;
 constexpr int UX_TMA_STAGES = 3;
 constexpr int UX_TMA_SMEM_BYTES = UX_TMA_STAGES * (UX_BM + UX_BN) * UX_KB * 4 + 64;
 
-enum UxMetric : int { UX_L1 = 0, UX_L2 = 1, UX_L2SQRT = 2, UX_LINF = 3, UX_CANBERRA = 4, UX_LP = 5 };
+enum UxMetric : int { UX_L1 = 0, UX_L2 = 1, UX_L2SQRT = 2, UX_LINF = 3, UX_CANBERRA = 4, UX_LP = 5,
+                      UX_HAMMING = 6, UX_KL = 7, UX_JS = 8 };
 
 struct UxParams {
   const float* x;
@@ -57,6 +58,19 @@ __device__ __forceinline__ void ux_acc(float& acc, float a, float b, float p)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
     acc = fmaf(d, r, acc);
+  } else if (kMetric == UX_HAMMING) {
+    acc += (a != b) ? 1.f : 0.f;  // final: / k
+  } else if (kMetric == UX_KL) {
+    // sum x log(x/y), terms with x == 0 contribute 0 ([RECALLED] reference epilogue halves the sum;
+    // see ux_fin).  log2 domain, scaled by ln 2 at the end; a zero-padded k tail adds 0.
+    const float t = a * (__log2f(a) - __log2f(b));
+    acc += (a == 0.f) ? 0.f : t;
+  } else if (kMetric == UX_JS) {
+    // sum x log(x/m) + y log(y/m), m = (x+y)/2; 0 log 0 = 0
+    const float lm = __log2f(0.5f * (a + b));
+    const float ta = a * (__log2f(a) - lm);
+    const float tb = b * (__log2f(b) - lm);
+    acc += ((a == 0.f) ? 0.f : ta) + ((b == 0.f) ? 0.f : tb);
   } else {
     const float d = fabsf(a - b);
     acc += exp2f(p * __log2f(d));  // d == 0 -> log2 = -inf -> exp2 = 0
@@ -68,6 +82,9 @@ __device__ __forceinline__ float ux_fin(float acc, float inv_p)
 {
   if (kMetric == UX_L2SQRT) return sqrtf(acc);
   if (kMetric == UX_LP) return exp2f(inv_p * __log2f(acc));
+  if (kMetric == UX_HAMMING) return acc * inv_p;                          // inv_p carries 1/k
+  if (kMetric == UX_KL) return 0.5f * 0.69314718056f * acc;              // 0.5 * sum x ln(x/y)
+  if (kMetric == UX_JS) return sqrtf(fmaxf(0.5f * 0.69314718056f * acc, 0.f));  // sqrt(JS divergence), natural log
   return acc;
 }
 

@@ -44,13 +44,17 @@ DISTANCE_TYPES = {
     "lp": DistanceType.LpUnexpanded,
     "minkowski": DistanceType.LpUnexpanded,
     "correlation": DistanceType.CorrelationExpanded,
+    "hellinger": DistanceType.HellingerExpanded,
+    "jensenshannon": DistanceType.JensenShannon,
+    "hamming": DistanceType.HammingUnexpanded,
+    "kl_divergence": DistanceType.KLDivergence,
+    "russellrao": DistanceType.RusselRaoExpanded,
 }
 
 SUPPORTED_DISTANCES = sorted(DISTANCE_TYPES)
 
 # metrics of the reference enum that are outside this engine's scope
-UNSUPPORTED = {"jaccard", "hellinger", "haversine", "braycurtis", "jensenshannon", "hamming",
-               "kl_divergence", "russellrao", "dice"}
+UNSUPPORTED = {"jaccard", "haversine", "braycurtis", "dice"}
 
 
 def resolve_metric(metric) -> DistanceType:

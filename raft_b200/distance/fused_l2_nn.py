@@ -10,6 +10,7 @@ import torch
 
 from .. import _lib
 from ..common import auto_convert_output, auto_sync_handle, cai_wrapper, device_ndarray
+from .distance_type import resolve_metric
 
 KVP_DTYPE = np.dtype([("key", np.int32), ("value", np.float32)])  # raft::KeyValuePair<int,float>
 
@@ -41,6 +42,22 @@ def fused_l2_nn(X, Y, sqrt=True, xn=None, yn=None, handle=None):
     yn_p = cai_wrapper(yn).data if yn is not None else None
     _lib.check(L.b2d_fused_l2_nn(handle.stream_ptr, kvp.data_ptr(), x_cai.data, k, y_cai.data, k, xn_p, yn_p,
                                  m, n, k, 1 if sqrt else 0, 1, ws.data_ptr(), ws.numel()))
+    return kvp[:, 0], kvp[:, 1].view(torch.float32)
+
+
+@auto_sync_handle
+def fused_distance_nn(X, Y, metric="euclidean", handle=None):
+    """raft::distance::fusedDistanceNN: (indices int32 [m], distances float32 [m]) of the nearest row
+    of Y for every row of X under metric in {sqeuclidean, euclidean, cosine, correlation}."""
+    x_cai, y_cai = _check_xy(X, Y)
+    m, k = x_cai.shape
+    n = y_cai.shape[0]
+    L = _lib.lib()
+    ws = handle.workspace(L.b2d_fused_l2_nn_workspace_bytes(m, n, k))
+    with torch.cuda.stream(handle.torch_stream):
+        kvp = torch.empty((m, 2), dtype=torch.int32, device=handle.device)
+    _lib.check(L.b2d_fused_distance_nn(handle.stream_ptr, kvp.data_ptr(), int(resolve_metric(metric)), x_cai.data, k,
+                                       y_cai.data, k, None, None, m, n, k, 1, ws.data_ptr(), ws.numel()))
     return kvp[:, 0], kvp[:, 1].view(torch.float32)
 
 

@@ -41,6 +41,25 @@ def main():
         d = cdist(x64, y64, "sqeuclidean")
         out[f"{name}_nn_idx"] = np.argmin(d, axis=1).astype(np.int32)
         out[f"{name}_nn_val"] = d.min(axis=1)
+    # probability-like inputs for the distribution metrics (rows sum to 1, a few exact zeros)
+    rng = np.random.default_rng(99)
+    px = rng.random((33, 21)); py = rng.random((27, 21))
+    px[rng.random(px.shape) < 0.1] = 0.0
+    py[rng.random(py.shape) < 0.1] = 0.0
+    px = (px / px.sum(1, keepdims=True)).astype(np.float32)
+    py = (py / py.sum(1, keepdims=True)).astype(np.float32)
+    out["prob_x"], out["prob_y"] = px, py
+    p64, q64 = px.astype(np.float64), py.astype(np.float64)
+    from scipy.special import rel_entr
+    out["prob_KLDivergence"] = 0.5 * np.array([[rel_entr(a, b).sum() for b in q64] for a in p64])  # reference halves the sum
+    m_ = 0.5 * (p64[:, None, :] + q64[None, :, :])
+    js = 0.5 * (rel_entr(p64[:, None, :], m_).sum(-1) + rel_entr(q64[None, :, :], m_).sum(-1))
+    out["prob_JensenShannon"] = np.sqrt(js)           # == scipy jensenshannon for normalised rows
+    out["prob_HellingerExpanded"] = np.sqrt(np.maximum(1.0 - np.sqrt(p64) @ np.sqrt(q64).T, 0.0))
+    bx = (rng.random((33, 40)) > 0.5).astype(np.float32); by = (rng.random((27, 40)) > 0.5).astype(np.float32)
+    out["bool_x"], out["bool_y"] = bx, by
+    out["bool_HammingUnexpanded"] = cdist(bx, by, "hamming")
+    out["bool_RusselRaoExpanded"] = cdist(bx.astype(bool), by.astype(bool), "russellrao")
     # reference known answers
     out["ref_argmin_in"] = np.array([0.1, 0.2, 0.3, 0.4, 0.4, 0.3, 0.2, 0.1, 0.2, 0.3, 0.5, 0.0],
                                     dtype=np.float32).reshape(3, 4)   # argmin.cu:71-72

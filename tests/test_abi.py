@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert os.path.exists(path)
     L = ctypes.CDLL(path)
     syms = header_symbols()
-    assert len(syms) >= 9
+    assert len(syms) >= 10
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/raft_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == syms
@@ -49,6 +49,7 @@ def test_workspace_queries():
     ws = L.b2d_pairwise_workspace_bytes(0, 0, 1000, 1000, 64)
     assert ws >= 2 * 1000 * 64 * 4 and ws < 4 * 1000 * 64 * 4 + 65536
     assert L.b2d_pairwise_workspace_bytes(11, 0, 10, 10, 4) == 2 ** 64 - 1   # Jaccard: not on this path
+    assert L.b2d_pairwise_workspace_bytes(16, 0, 10, 10, 4) == 0             # Hamming: SIMT path, no scratch
     assert L.b2d_fused_l2_nn_workspace_bytes(100, 200, 96) > 300 * 96 * 4
 
 
@@ -58,7 +59,7 @@ def test_invalid_arguments_are_reported_not_crashed():
     assert rc == _lib.B2D_ERR_INVALID_ARG and b"null" in L.b2d_last_error()
     rc = L.b2d_pairwise_distance(None, 0, 0, 256, 4, 256, 8, 256, 8, 4, 4, 8, 1, 2.0, None, 0)
     assert rc == _lib.B2D_ERR_INVALID_ARG          # ldx < k
-    rc = L.b2d_pairwise_distance(None, 12, 0, 256, 8, 256, 8, 256, 8, 4, 4, 8, 1, 2.0, None, 0)
+    rc = L.b2d_pairwise_distance(None, 13, 0, 256, 8, 256, 8, 256, 8, 4, 4, 8, 1, 2.0, None, 0)
     assert rc == _lib.B2D_ERR_UNSUPPORTED
     rc = L.b2d_pairwise_distance(None, 0, 0, 256, 8, 256, 8, 256, 8, 4, 4, 8, 1, 2.0, None, 0)
     assert rc == _lib.B2D_ERR_WORKSPACE

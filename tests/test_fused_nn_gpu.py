@@ -6,7 +6,8 @@ import torch
 import oracle
 from raft_b200 import _lib
 from raft_b200.common import DeviceResources
-from raft_b200.distance import fused_l2_nn, fused_l2_nn_argmin, fused_l2_nn_sharded, shard_bounds
+from raft_b200.distance import (fused_distance_nn, fused_l2_nn, fused_l2_nn_argmin, fused_l2_nn_sharded,
+                                shard_bounds)
 
 pytestmark = pytest.mark.gpu
 
@@ -47,6 +48,24 @@ def test_golden_nn(golden):
         gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
         assert (gi.cpu().numpy() == golden[f"{case}_nn_idx"]).all()
         assert oracle.match_approx(gv.cpu().numpy(), golden[f"{case}_nn_val"], 1e-4)[0]
+
+
+@pytest.mark.parametrize("metric", ["sqeuclidean", "euclidean", "cosine", "correlation"])
+def test_fused_distance_nn_metrics(metric):
+    """raft::distance::fusedDistanceNN (SURVEY.md 8(f1)): arg-min under L2 and the cosine family."""
+    x, y = blobs(900, 2100, 64, seed=5)
+    mt = {"sqeuclidean": oracle.DistanceType.L2Expanded, "euclidean": oracle.DistanceType.L2SqrtExpanded,
+          "cosine": oracle.DistanceType.CosineExpanded, "correlation": oracle.DistanceType.CorrelationExpanded}[metric]
+    d = oracle.pairwise_distance(x, y, mt)
+    ri, rv = d.argmin(axis=1), d.min(axis=1)
+    gi, gv = fused_distance_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), metric=metric)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    bad = np.nonzero(gi != ri)[0]
+    assert len(bad) <= 2
+    for i in bad:   # near-ties only
+        assert abs(d[i, gi[i]] - rv[i]) <= 1e-5 * max(rv[i], 1e-3)
+    ok, msg = oracle.match_approx(gv, rv, 1e-4)
+    assert ok, msg
 
 
 def test_ties_go_to_smaller_index():

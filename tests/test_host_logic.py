@@ -41,6 +41,8 @@ def test_metric_strings():
     assert resolve_metric("minkowski") == DistanceType.LpUnexpanded
     assert resolve_metric("L2Unexpanded") == DistanceType.L2Unexpanded
     assert resolve_metric(8) == DistanceType.Canberra
+    assert resolve_metric("hamming") == DistanceType.HammingUnexpanded
+    assert resolve_metric("kl_divergence") == DistanceType.KLDivergence
     with pytest.raises(ValueError):
         resolve_metric("jaccard")
     assert set(DISTANCE_TYPES) >= {"l2", "l1", "cosine", "correlation", "canberra", "inner_product", "lp"}

@@ -18,6 +18,19 @@ def test_numpy_oracle_matches_golden(golden, case, metric):
     np.testing.assert_allclose(got, golden[f"{case}_{metric}"], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", ["prob_KLDivergence", "prob_JensenShannon", "prob_HellingerExpanded",
+                                  "bool_HammingUnexpanded", "bool_RusselRaoExpanded"])
+def test_distribution_and_boolean_metrics_golden(golden, name):
+    pre, metric = name.split("_")
+    x, y = golden[f"{pre}_x"], golden[f"{pre}_y"]
+    for impl in (oracle.pairwise_distance, coracle.pairwise_distance):
+        got = impl(x, y, DT[metric])
+        ref = golden[name]
+        fin = np.isfinite(ref)
+        np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-9, atol=1e-9)
+        assert (np.isinf(got) == np.isinf(ref)).all()
+
+
 @pytest.mark.parametrize("case", ["small", "cfg1"])
 def test_minkowski_golden(golden, case):
     got = oracle.pairwise_distance(golden[f"{case}_x"], golden[f"{case}_y"], DT.LpUnexpanded, 3.0)

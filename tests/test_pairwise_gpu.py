@@ -72,6 +72,29 @@ def test_uniform_data(metric):
     check(run(x, y, metric), oracle.pairwise_distance(x, y, metric))
 
 
+@pytest.mark.parametrize("name", ["prob_KLDivergence", "prob_JensenShannon", "prob_HellingerExpanded",
+                                  "bool_HammingUnexpanded", "bool_RusselRaoExpanded"])
+def test_distribution_and_boolean_metrics(golden, name):
+    # the remaining dense metrics of the enum, against the golden fixtures
+    pre, metric = name.split("_")
+    x, y = golden[f"{pre}_x"], golden[f"{pre}_y"]
+    got = run(x, y, DT[metric]).astype(np.float64)
+    ref = golden[name]
+    fin = np.isfinite(ref)
+    assert (np.isinf(got) == np.isinf(ref)).all()
+    ok, msg = oracle.match_approx(got[fin], ref[fin], EPS)
+    assert ok, msg
+    # and a larger ragged shape against the oracle
+    rng = np.random.default_rng(4)
+    if pre == "prob":
+        a = rng.random((300, 70)); b = rng.random((260, 70))
+        a /= a.sum(1, keepdims=True); b /= b.sum(1, keepdims=True)
+    else:
+        a = (rng.random((300, 70)) > 0.5); b = (rng.random((260, 70)) > 0.5)
+    a, b = a.astype(np.float32), b.astype(np.float32)
+    check(run(a, b, DT[metric]), oracle.pairwise_distance(a, b, DT[metric]))
+
+
 def test_canberra_zero_over_zero_is_zero():
     rng = np.random.default_rng(9)
     x = rng.standard_normal((150, 40)).astype(np.float32)
@@ -225,6 +248,8 @@ def test_error_behaviour():
         pairwise_distance(a, b)
     with pytest.raises(ValueError):
         pairwise_distance(a, a, metric="jaccard")
+    with pytest.raises(ValueError):
+        pairwise_distance(a, a, metric="haversine")
     with pytest.raises(TypeError):
         pairwise_distance(a, a.double())
     with pytest.raises((ValueError, LogicError)):
