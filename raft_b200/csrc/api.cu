@@ -332,6 +332,7 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
   if (m == 0 || n == 0) return B2D_OK;
+  if (k == 0) return fail(B2D_ERR_INVALID_ARG, "k must be positive");
   if (!x || !y || !dist) return fail(B2D_ERR_INVALID_ARG, "null x / y / dist");
   if (m > 0x7fffffffll * 128 || n > 0x7fffffffll || k > (1 << 24)) return fail(B2D_ERR_INVALID_ARG, "extent too large");
   if (row_major) {
@@ -433,6 +434,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
   if (m == 0) return B2D_OK;
+  if (k == 0) return fail(B2D_ERR_INVALID_ARG, "k must be positive");
   if (!keys || !x || (n > 0 && !y)) return fail(B2D_ERR_INVALID_ARG, "null keys / x / y");
   if (ldx < k || ldy < k) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than k");
   if (n + idx_offset > 0xFFFFFFFFll || idx_offset < 0) return fail(B2D_ERR_INVALID_ARG, "index range exceeds 32 bits");
