@@ -193,6 +193,35 @@ __global__ void __launch_bounds__(UX_THREADS, 1) unexpanded_simt_kernel(const Ux
   }
 }
 
+__device__ __forceinline__ uint64_t ux_pk(float lo, float hi)
+{
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ux_unpk(uint64_t v, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ux_add2(uint64_t a, uint64_t b)
+{
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t ux_fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float ux_max3(float a, float b, float c)
+{
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // TMA-fed variant (rows 16-byte aligned, k % 4 == 0, row-major): the same 128x128x32 tiles arrive
 // by cp.async.bulk.tensor with SWIZZLE_128B -- the XOR pattern the manual loader writes -- through
 // a 3-stage mbarrier ring, so no thread spends registers or issue slots on staging and OOB rows /
@@ -232,11 +261,18 @@ unexpanded_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (tid == 0)
     for (int kb = 0; kb < UX_TMA_STAGES - 1 && kb < nkb; ++kb) issue(kb);
 
+  // L2 / L2Sqrt: packed f32x2 math (FADD2 + FFMA2: one issue slot per pair-element instead of two);
+  // every output keeps an (even-k, odd-k) pair of partial sums that is folded at the end.
+  constexpr bool kPackedL2 = (kMetric == UX_L2 || kMetric == UX_L2SQRT);
   float acc[8][8];
+  uint64_t acc2[kPackedL2 ? 8 : 1][kPackedL2 ? 8 : 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      acc[i][j] = 0.f;
+      if (kPackedL2) acc2[i % (kPackedL2 ? 8 : 1)][j % (kPackedL2 ? 8 : 1)] = 0ull;
+    }
 
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % UX_TMA_STAGES;
@@ -255,18 +291,50 @@ unexpanded_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       for (int j = 0; j < 8; ++j) {
         const int row  = tx + 16 * j;
         const float4 b = *reinterpret_cast<const float4*>(&by[row * UX_KB + ((c4 ^ (row & 7)) << 2)]);
+        if (kPackedL2) {
+          const uint64_t nb0 = ux_pk(-b.x, -b.y), nb1 = ux_pk(-b.z, -b.w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ux_acc<kMetric>(acc[i][j], a[i].x, b.x, p.p);
-          ux_acc<kMetric>(acc[i][j], a[i].y, b.y, p.p);
-          ux_acc<kMetric>(acc[i][j], a[i].z, b.z, p.p);
-          ux_acc<kMetric>(acc[i][j], a[i].w, b.w, p.p);
+          for (int i = 0; i < 8; ++i) {
+            const uint64_t d0 = ux_add2(ux_pk(a[i].x, a[i].y), nb0);
+            const uint64_t d1 = ux_add2(ux_pk(a[i].z, a[i].w), nb1);
+            uint64_t& t       = acc2[i % (kPackedL2 ? 8 : 1)][j % (kPackedL2 ? 8 : 1)];
+            t                 = ux_fma2(d0, d0, t);
+            t                 = ux_fma2(d1, d1, t);
+          }
+        } else if (kMetric == UX_LINF) {
+          const uint64_t nb0 = ux_pk(-b.x, -b.y), nb1 = ux_pk(-b.z, -b.w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float d0, d1, d2, d3;
+            ux_unpk(ux_add2(ux_pk(a[i].x, a[i].y), nb0), d0, d1);
+            ux_unpk(ux_add2(ux_pk(a[i].z, a[i].w), nb1), d2, d3);
+            acc[i][j] = ux_max3(acc[i][j], fabsf(d0), fabsf(d1));
+            acc[i][j] = ux_max3(acc[i][j], fabsf(d2), fabsf(d3));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            ux_acc<kMetric>(acc[i][j], a[i].x, b.x, p.p);
+            ux_acc<kMetric>(acc[i][j], a[i].y, b.y, p.p);
+            ux_acc<kMetric>(acc[i][j], a[i].z, b.z, p.p);
+            ux_acc<kMetric>(acc[i][j], a[i].w, b.w, p.p);
+          }
         }
       }
     }
     // every thread is done with the stage that block kb-1 used: refill it with block kb+STAGES-1
     __syncthreads();
     if (tid == 0 && kb + UX_TMA_STAGES - 1 < nkb) issue(kb + UX_TMA_STAGES - 1);
+  }
+  if (kPackedL2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float lo, hi;
+        ux_unpk(acc2[i % (kPackedL2 ? 8 : 1)][j % (kPackedL2 ? 8 : 1)], lo, hi);
+        acc[i][j] = lo + hi;
+      }
   }
 
 #pragma unroll
