@@ -46,6 +46,20 @@ void pairwise_distance(raft::resources const& handle, const DataT* x, const Data
                                           static_cast<float>(metric_arg), ws, need));
 }
 
+// overload with a caller-supplied workspace (the reference took an rmm::device_uvector<char>&;
+// here: any device buffer of at least b2d_pairwise_workspace_bytes() bytes)
+template <typename DataT, typename IdxT = int>
+void pairwise_distance(raft::resources const& handle, const DataT* x, const DataT* y, DataT* dist, IdxT m, IdxT n,
+                       IdxT k, void* workspace, size_t workspace_bytes, raft::distance::DistanceType metric,
+                       bool isRowMajor = true, DataT metric_arg = 2.0f)
+{
+  const int64_t ldx = isRowMajor ? k : m, ldy = isRowMajor ? k : n, ldd = isRowMajor ? n : m;
+  detail::b2d_check(b2d_pairwise_distance(raft::resource::get_cuda_stream(handle), static_cast<int>(metric),
+                                          detail::b2d_dtype<DataT>(), x, ldx, y, ldy, dist, ldd, m, n, k,
+                                          isRowMajor ? 1 : 0, static_cast<float>(metric_arg), workspace,
+                                          workspace_bytes));
+}
+
 template <typename DataT, typename IdxT, typename Layout>
 void pairwise_distance(raft::resources const& handle, raft::device_matrix_view<const DataT, IdxT, Layout> x,
                        raft::device_matrix_view<const DataT, IdxT, Layout> y,

@@ -51,6 +51,26 @@ int main()
       }
       if (hn[i].key != best || std::fabs(hn[i].value - bv) > 1e-4 * std::fmax(bv, 1.0)) ++bad;
     }
+    // legacy stream-only fusedL2NN signature + fusedDistanceNN (cosine)
+    raft::distance::fusedL2NNMinReduce<float, raft::KeyValuePair<int, float>, int>(nn, x, y, nullptr, nullptr, m, n, k,
+                                                                                    nullptr, false, true, s);
+    std::vector<raft::KeyValuePair<int, float>> hn2(m), hc(m);
+    cudaMemcpyAsync(hn2.data(), nn, m * sizeof(*nn), cudaMemcpyDeviceToHost, s);
+    raft::distance::fusedDistanceNNMinReduce<float, raft::KeyValuePair<int, float>, int>(
+      nn, x, y, nullptr, nullptr, m, n, k, nullptr, false, true, true, raft::distance::DistanceType::CosineExpanded, 0.f, handle);
+    cudaMemcpyAsync(hc.data(), nn, m * sizeof(*nn), cudaMemcpyDeviceToHost, s);
+    raft::resource::sync_stream(handle);
+    for (int i = 0; i < m; ++i) {
+      if (hn2[i].key != hn[i].key || hn2[i].value != hn[i].value) ++bad;
+      int best = 0; double bv = 1e300;
+      for (int j = 0; j < n; ++j) {
+        double dot = 0, na = 0, nb = 0;
+        for (int t = 0; t < k; ++t) { dot += (double)hx[i * k + t] * hy[j * k + t]; na += (double)hx[i * k + t] * hx[i * k + t]; nb += (double)hy[j * k + t] * hy[j * k + t]; }
+        double c = 1.0 - dot / std::sqrt(na * nb);
+        if (c < bv) { bv = c; best = j; }
+      }
+      if (hc[i].key != best || std::fabs(hc[i].value - bv) > 1e-4 * std::fmax(std::fabs(bv), 1e-2)) ++bad;
+    }
     // error convention: unsupported metric -> raft::logic_error
     bool threw = false;
     try { raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::JaccardExpanded); }

@@ -117,3 +117,14 @@ def test_minloc_allreduce_world2_gloo(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_pylibraft_alias_namespace():
+    """`from pylibraft.distance import pairwise_distance` keeps working (drop-in alias package)."""
+    import pylibraft.common
+    import pylibraft.config
+    import pylibraft.distance as d
+    import raft_b200.distance as r
+    assert d.pairwise_distance is r.pairwise_distance and d.fused_l2_nn_argmin is r.fused_l2_nn_argmin
+    assert "euclidean" in d.DISTANCE_TYPES and callable(pylibraft.config.set_output_as)
+    assert pylibraft.common.DeviceResources is not None
