@@ -33,8 +33,18 @@ def test_random_shapes_all_paths():
             got = outp[:, :n].cpu().numpy()
         else:
             got = pairwise_distance(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), metric=metric).copy_to_host()
-        ok, msg = oracle.match_approx(got, oracle.pairwise_distance(x, y, metric), 1e-4)
-        assert ok, (it, m, n, k, metric, msg)
+        ref = oracle.pairwise_distance(x, y, metric)
+        ok = oracle.compare_approx(got, ref, 1e-4)
+        if metric in (DT.L2Expanded, DT.L2SqrtExpanded):
+            # expanded form in fp32: xn + yn - 2xy cannot resolve d^2 below a few ulp of (xn + yn); pairs
+            # that close (random k = 1 collisions) are held to that floor instead of 1e-4 relative --
+            # the same limit the reference's expanded fp32 kernels have
+            sq = metric == DT.L2SqrtExpanded
+            g2 = got.astype(np.float64) ** 2 if sq else got.astype(np.float64)
+            r2 = ref ** 2 if sq else ref
+            floor = 8 * 2.0 ** -24 * (oracle.row_norm_sq(x)[:, None] + oracle.row_norm_sq(y)[None, :])
+            ok |= np.abs(g2 - r2) <= floor
+        assert ok.all(), (it, m, n, k, metric, int((~ok).sum()), np.argwhere(~ok)[0])
 
 
 def test_random_shapes_fused_nn():
