@@ -1,17 +1,19 @@
 // K1 / K3: expanded-form metrics on tcgen05 tensor cores (sm_100a).
 //
 // Replaces the pair loop of raft::distance::pairwise_distance for L2Expanded / L2SqrtExpanded /
-// CosineExpanded / CorrelationExpanded / InnerProduct and of raft::distance::fusedL2NN
-// (SURVEY.md 8(a2),(a3),(a5); the reference's last implementation was a CUTLASS 3xTF32 mma.sync
-// kernel, CHANGELOG.md:1443,1140 -- this is not a port of it).
+// CosineExpanded / CorrelationExpanded / InnerProduct (+ Hellinger, RusselRao) and of
+// raft::distance::fusedL2NN / fusedDistanceNN (SURVEY.md 8(a2),(a3),(a5),(f1); the reference's last
+// implementation was a CUTLASS 3xTF32 mma.sync kernel, CHANGELOG.md:1443,1140 -- this is not a
+// port of it).
 //
-// Numerics: fp32 inputs are pre-split (prep.cuh) into fp16 hi/lo with a power-of-two row scale;
-// acc = hi*hi + hi*lo + lo*hi accumulates in fp32 in TMEM (products of fp16 pairs are exact in
-// fp32), i.e. ~22 significant bits per operand -- fp32-grade, same idea as the reference's 3xTF32
-// but at the 2x higher kind::f16 rate and with 4 B/element staged instead of 8.  The tensor core
-// aligns every product to the accumulator's exponent and truncates, so the error grows with the
-// number of MMAs that touch a LARGE accumulator: the 2^-11-sized cross terms must not be mixed
-// into the running hi*hi sum (measured: 1.0e-4 -> 4.5e-5 max relative error at k = 128).
+// Numerics: fp32 inputs are pre-split (prep.cuh) into fp16 hi/lo with one power-of-two scale per
+// matrix; acc = hi*hi + hi*lo + lo*hi accumulates in fp32 in TMEM (products of fp16 pairs are
+// exact in fp32), i.e. ~22 significant bits per operand -- fp32-grade, same idea as the
+// reference's 3xTF32 but at the 2x higher kind::f16 rate and with 4 B/element staged instead of 8.
+// The tensor core aligns every product to the accumulator's exponent and truncates, so the error
+// grows with the number of MMAs that touch a LARGE accumulator: the 2^-11-sized cross terms must
+// not be mixed into the running hi*hi sum (measured: 1.0e-4 -> 4.5e-5 max relative error at k = 128).
+// Operands that are exact in fp16 (fp16 inputs, small integers) skip the cross terms altogether.
 //
 // Structure (one persistent CTA per SM, 320 threads):
 //   warp 0     TMA producer    cp.async.bulk.tensor 2-D, SWIZZLE_128B, mbarrier complete_tx
@@ -21,23 +23,28 @@
 // Work item = (256-row block of y, run of 128-row tiles of x); tile = 128 x 256 outputs.
 //
 //  kResident (k <= 128): the y block (all of K, <= 128 KB) stays in shared memory for the whole run;
-//    x tiles stream through a 6-stage ring.  Each tile is a TWO-PASS N=256 MMA sequence into ONE
-//    256-column accumulator: first every cross term of every k-block (accumulator still tiny), then
-//    every hi*hi term -- the same "2 large-accumulator MMAs per k-block" as separate accumulators,
-//    but with N=256 instructions (96 B/clk of shared-memory operand reads instead of 128 B/clk for
-//    N=128) and with TMEM double-buffered across tiles (2 x 256 columns).
+//    x tiles stream through a ring of 16 KB stages (6, or 4 when the TMA-store staging block takes
+//    the other 32 KB).  Each tile is a TWO-PASS N=256 MMA sequence into ONE 256-column accumulator:
+//    first every cross term of every k-block (accumulator still tiny), then every hi*hi term --
+//    2 large-accumulator MMAs per k-block, N=256 instructions (96 B/clk of shared-memory operand
+//    reads instead of 128 B/clk for N=128), TMEM double-buffered across tiles (2 x 256 columns).
 //  !kResident (k > 128): both operands stream per k-block (4 stages of 48 KB); a tile is two 128-column
 //    halves, each with its own `main` and `cross` accumulator (4 x 128 = all 512 TMEM columns).
 //
-// Epilogue: tcgen05.ld.16x256b.x8 gives each thread 2 adjacent columns of 2 rows per 8-column
-// group (the m16n8 fragment), so results go from registers STRAIGHT to global memory: a warp-wide
-// 8-byte store writes 8 rows x one full 32-byte sector -- no shared-memory staging (shared-memory
-// bandwidth is the scarce resource: tcgen05.mma reads its operands from it at up to 128 B/clk).
-//   d = acc * c + (t_x[i] + t_y[j]) on packed f32x2 pipes (FADD2/FFMA2; c is one scalar), then
-//   EPI_STORE   clamp / sqrt / st.global.cs.v2
-//   EPI_MINLOC  per-row running min / arg-min (FMNMX3 tree per 16 values, rare index rescan), quad
-//               shuffle reduce, one packed 64-bit atomicMin per row per 128 columns, skipped when
-//               the row's current global key is already smaller.
+// Epilogues: d = acc * c + (t_x[i] + t_y[j]) on packed f32x2 pipes (FADD2/FFMA2; c is one scalar)
+//   EPI_STORE, kTma   (dist 16-byte aligned, n % 4 == 0) tcgen05.ld.32x32b (thread == row), clamp /
+//                     sqrt, 32x32 block staged in shared memory with the 128-byte XOR swizzle, one
+//                     TMA tensor store per warp per 32 columns -- whole 128-byte lines, hardware
+//                     edge clipping.  Measured: 5.9 TB/s is the ceiling of every store mechanism
+//                     for this tile footprint at full clock (scripts/probes/).
+//   EPI_STORE, !kTma  tcgen05.ld.16x256b.x8 gives each thread 2 adjacent columns of 2 rows per
+//                     8-column group (the m16n8 fragment): registers go straight to global memory,
+//                     a warp-wide 8-byte store writes 8 rows x one full 32-byte sector.  Also the
+//                     read-modify-write path of K-chunked accumulation (k > 320).
+//   EPI_MINLOC        16x256b fragments; per row an FMNMX3 tree over the thread's 16 values is
+//                     compared with the row's current global best (read from keys at tile start:
+//                     an upper bound, keys only decrease); only a candidate that can change the
+//                     result takes the slow path (smallest-column scan + packed 64-bit atomicMin).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
