@@ -112,10 +112,10 @@ int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float
                           const float* y, int64_t ldy, const float* xn, const float* yn, int64_t m,
                           int64_t n, int64_t k, int init_out, void* workspace, size_t workspace_bytes);
 
-/* Multi-GPU building blocks.  keys[i] = (order-preserving bits of (|y_j|^2 - 2 x_i.y_j) << 32)
+/* Multi-GPU building blocks.  keys[i] = (order-preserving bits of ||x_i - y_j||^2 << 32)
  * | (j + idx_offset), reduced with signed 64-bit MIN: over this GPU's y shard here, then across
  * GPUs by the caller's all-reduce(INT64, MIN).  init_keys != 0 resets keys to +max first.
- * The workspace retains |x_i|^2 for b2d_fused_l2_nn_finalize (same workspace, same m). */
+ * b2d_fused_l2_nn_finalize unpacks (clamp at 0, optional sqrt). */
 int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y,
                          int64_t ldy, const float* xn, const float* yn, int64_t m, int64_t n,
                          int64_t k, int64_t idx_offset, int init_keys, void* workspace,

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 #include <mutex>
 #include <string>
 
@@ -91,6 +92,10 @@ struct TcWorkspace {
   unsigned* gmax;  // [2]
   float* coef;     // [1]
   unsigned* has_lo;  // [1]
+  float* thr;        // [m]    screened NN: per-row upper bound
+  int2* cand;        // [cap]  screened NN: candidate list
+  unsigned* cand_cnt;  // [1] (+ overflow flag right behind it)
+  unsigned cand_cap;
   size_t bytes;
 };
 
@@ -112,6 +117,12 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   w.has_lo = w.gmax + 3;
   w.xt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4));
   w.keys = reinterpret_cast<long long*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
+  // screened fusedL2NN scratch: thresholds, counters, candidate list (64 per row: ~50 expected on
+  // clustered data; overflow falls back to the exact pass on the device, never to a wrong answer)
+  w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(64 * m + (1 << 16), 0x7fffffff)) : 0u;
+  w.thr      = reinterpret_cast<float*>(c + take(with_keys ? static_cast<size_t>(m) * 4 : 0));
+  w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 16 : 0));
+  w.cand     = reinterpret_cast<int2*>(c + take(static_cast<size_t>(w.cand_cap) * 8));
   w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
   w.xop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(m) * nkb * 128));
   w.yop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(n) * nkb * 128));
@@ -200,14 +211,19 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.nkb     = nkb_chunk ? nkb_chunk : nkb_total;
   p.tiles_m = static_cast<int>((p.m + TC_BM - 1) / TC_BM);
   p.tiles_n = static_cast<int>((p.n + TC_BN - 1) / TC_BN);
-  int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  if (p.sel_mode == 0) p.tiles_sel = p.tiles_n;
+  else {
+    const int first = (p.tiles_n + p.sel_s - 1) / p.sel_s;  // blocks with index % sel_s == 0
+    p.tiles_sel     = p.sel_mode == 1 ? first : p.tiles_n - first;
+  }
+  int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_sel;
   int64_t chunk = total / (static_cast<int64_t>(sms) * 6);
   if (chunk < 1) chunk = 1;
   if (chunk > 32) chunk = 32;
   if (chunk > p.tiles_m) chunk = p.tiles_m;
   p.chunk    = static_cast<int>(chunk);
   p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
-  p.n_items  = static_cast<int64_t>(p.tiles_n) * p.chunks_m;
+  p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
   p.xt       = w.xt;
   p.yt       = w.yt;
   p.coef     = w.coef;
@@ -224,6 +240,10 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   if (epi == EPI_MINLOC) {
     return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
                     : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
+  }
+  if (epi == EPI_SCREEN) {
+    if (!resident) return fail(B2D_ERR_UNSUPPORTED, "internal: screening needs the resident kernel");
+    return launch_tc_inst<true, EPI_SCREEN, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
   // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
   // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
@@ -453,6 +473,33 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
+  const int nkb = static_cast<int>((k + 31) / 32);
+  static const bool screen_off = getenv("B2D_NN_SCREEN") != nullptr && atoi(getenv("B2D_NN_SCREEN")) == 0;
+  const bool screen = mode == PREP_L2 && nkb <= TC_MAX_RES_KB && n >= 16384 && !screen_off;
+  if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+
+  // Screened search (see expanded_tc.cuh): exact on every 8th y block -> bound; coarse 1-product pass
+  // over the rest -> candidates; exact re-evaluation of the candidates; exact fallback only if the
+  // candidate list overflowed (decided on the device: no host round trip).
+  constexpr int kSel = 8;
+  p.sel_mode = 1; p.sel_s = kSel;
+  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+  if (rc) return rc;
+  unsigned* overflow = w.cand_cnt + 1;
+  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.thr, w.cand,
+                                                                         w.cand_cnt, overflow, m, n, idx_offset);
+  B2D_CUDA(cudaGetLastError());
+  p.sel_mode = 2; p.thr = w.thr; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
+  p.overflow = overflow; p.force_no_lo = 1;
+  rc = launch_tc(s, w, p, k, EPI_SCREEN, POST_NONE);
+  if (rc) return rc;
+  int sms = 0, cc = 0;
+  rc = device_sms(&sms, &cc);
+  if (rc) return rc;
+  nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
+                                          ldy, static_cast<int>(k), idx_offset);
+  B2D_CUDA(cudaGetLastError());
+  p.force_no_lo = 0; p.run_flag = overflow;  // runs only if candidates were dropped
   return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 }
 
@@ -474,7 +521,7 @@ int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys,
   if (workspace_bytes < 1024 + static_cast<size_t>(m) * 4) return fail(B2D_ERR_WORKSPACE, "workspace too small");
   TcWorkspace w = tc_layout(const_cast<void*>(workspace), m, 0, 0, true);
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
-    reinterpret_cast<KvpIF*>(out), reinterpret_cast<const long long*>(keys), w.xt, m, do_sqrt, 0);
+    reinterpret_cast<KvpIF*>(out), reinterpret_cast<const long long*>(keys), m, do_sqrt, 0);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -495,7 +542,7 @@ int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, 
                                 workspace, workspace_bytes);
   if (rc) return rc;
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
-    reinterpret_cast<KvpIF*>(out), w.keys, w.xt, m, do_sqrt, init_out ? 0 : 1);
+    reinterpret_cast<KvpIF*>(out), w.keys, m, do_sqrt, init_out ? 0 : 1);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -522,7 +569,7 @@ int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float
                          workspace, workspace_bytes, PREP_COSINE, metric == B2D_CorrelationExpanded ? 1 : 0);
   if (rc) return rc;
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
-    reinterpret_cast<KvpIF*>(out), w.keys, w.xt, m, 0, init_out ? 0 : 1);
+    reinterpret_cast<KvpIF*>(out), w.keys, m, 0, init_out ? 0 : 1);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }

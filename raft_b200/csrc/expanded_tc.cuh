@@ -64,13 +64,15 @@ constexpr int TC_MAX_STAGES  = 6;
 constexpr int TC_EPI_WARPS   = 8;
 constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
 
-enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1 };
+enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1, EPI_SCREEN = 2 };
 enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
 
 struct TcParams {
   int64_t m, n;
   int nkb;                // k-blocks of 32 source columns
   int tiles_m, tiles_n;   // ceil(m/128), ceil(n/256)
+  int tiles_sel;          // y blocks this launch visits (all of them unless sel_mode != 0)
+  int sel_mode, sel_s;    // 0: every y block; 1: blocks with index % sel_s == 0; 2: the others
   int chunk;              // m-tiles per work item
   int chunks_m;           // ceil(tiles_m/chunk)
   int64_t n_items;        // tiles_n * chunks_m
@@ -84,15 +86,30 @@ struct TcParams {
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
   int pair_ok;            // dist 8-byte aligned and ldd even -> st.v2
   int acc_mode;           // K-chunked accumulation: 0 single pass, 1 first chunk (raw store), 2 middle (+=), 3 last (+=, post)
-  // EPI_MINLOC
-  long long* keys;        // [m] packed (ordered float bits << 32 | index)
+  // EPI_MINLOC / EPI_SCREEN
+  long long* keys;        // [m] packed (ordered bits of the distance << 32 | index)
   int64_t idx_offset;
+  const float* thr;       // EPI_SCREEN: [m] upper bound of the row's true minimum distance
+  int2* cand;             // EPI_SCREEN: candidate (row, column) list
+  unsigned* cand_cnt;     //             its fill counter ...
+  unsigned cand_cap;      //             ... capacity ...
+  unsigned* overflow;     //             ... and overflow flag (then the exact pass re-runs)
+  const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
+  int force_no_lo;        // coarse pass: hi*hi only
 };
 
 constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES_RES * TC_A_BYTES;  // 224 KB
 static_assert((size_t)TC_STAGES_STR * (TC_A_BYTES + TC_B_BYTES) <= TC_SMEM_OPERANDS, "streaming carve fits");
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_BN * 4 + 256;
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + 2 * TC_BN * 4 + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
+
+// index of the s-th selected y block (see TcParams::sel_mode)
+__device__ __forceinline__ int sel_to_blk(int s, int mode, int S)
+{
+  if (mode == 0) return s;
+  if (mode == 1) return s * S;
+  return s + s / (S - 1) + 1;
+}
 
 // float -> int whose signed order equals the float order
 __device__ __forceinline__ int ordered_bits(float v)
@@ -152,6 +169,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   // tensor store per warp per 32 columns (whole 128-byte lines); the 32 KB of staging replace two
   // of the six x stages.
   constexpr int kStages = kResident ? (kTma ? TC_STAGES_RES - 2 : TC_STAGES_RES) : TC_STAGES_STR;
+  if (p.run_flag != nullptr && __ldg(p.run_flag) == 0u) return;  // conditional launch (no host round trip)
   extern __shared__ __align__(1024) uint8_t smem[];
   // SWIZZLE_128B atoms need 1024-byte alignment; the dynamic window starts 1024-aligned (no static
   // shared memory in this kernel).  Checked, not assumed: a misaligned base traps.
@@ -160,7 +178,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES_STR * TC_B_BYTES);
   float* stg      = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS - TC_EPI_WARPS * 4096);  // kTma only
   float* col_tb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);  // [256] t_y of this y block
-  uint64_t* bars  = reinterpret_cast<uint64_t*>(col_tb + TC_BN);
+  float* col_ny   = col_tb + TC_BN;                                     // [256] EPI_SCREEN: scaled |y_j|
+  uint64_t* bars  = reinterpret_cast<uint64_t*>(col_ny + TC_BN);
   uint64_t* afull = bars;                       // [TC_MAX_STAGES]
   uint64_t* aempty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
   uint64_t* bfull = bars + 2 * TC_MAX_STAGES;   // [TC_MAX_RES_KB]
@@ -198,8 +217,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint64_t pol = ptx::policy_evict_last();
     uint32_t a_it = 0, it_local = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-      const int n_blk = static_cast<int>(item % p.tiles_n);
-      const int ch    = static_cast<int>(item / p.tiles_n);
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int ch    = static_cast<int>(item / p.tiles_sel);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
       for (int mt = mt0; mt < mt1; ++mt) {
@@ -228,9 +247,9 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // descriptor start-address units are 16 B; inside the 128-B swizzled row of a k-block:
     //   hi k[0,16) +0, hi k[16,32) +2, lo k[0,16) +4, lo k[16,32) +6
     uint32_t a_it = 0, t_it = 0, it_local = 0;
-    const bool has_lo = __ldg(p.has_lo) != 0u;
+    const bool has_lo = !p.force_no_lo && __ldg(p.has_lo) != 0u;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-      const int ch  = static_cast<int>(item / p.tiles_n);
+      const int ch  = static_cast<int>(item / p.tiles_sel);
       const int mt0 = ch * p.chunk;
       const int mt1 = min(mt0 + p.chunk, p.tiles_m);
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
@@ -319,21 +338,28 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int tq   = lane & 3;          // fragment column pair inside an 8-column group
     uint32_t t_it  = 0;
     const float cf     = __ldg(p.coef);
-    const bool add_cross = !kResident && __ldg(p.has_lo) != 0u;  // streaming layout keeps cross terms apart
+    const bool add_cross = !kResident && !p.force_no_lo && __ldg(p.has_lo) != 0u;  // streaming layout keeps cross terms apart
     const uint64_t pol_st = ptx::policy_evict_first();
     const uint64_t cf2 = pk(cf, cf);
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int n_blk = static_cast<int>(item % p.tiles_n);
-      const int ch    = static_cast<int>(item / p.tiles_n);
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int ch    = static_cast<int>(item / p.tiles_sel);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
       // per-column epilogue terms of this y block (shared by every tile of the item)
       ptx::bar_sync(1, 32 * TC_EPI_WARPS);
       {
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
-        float tv = kEpi == EPI_MINLOC ? __int_as_float(0x7f800000) : 0.f;  // +inf: never the arg-min
+        float tv = kEpi != EPI_STORE ? __int_as_float(0x7f800000) : 0.f;  // +inf: never the arg-min
         if (gj < p.n) tv = __ldg(&p.yt[gj]);
         if (kEpi == EPI_STORE && p.acc_mode >= 2) tv = 0.f;  // the t terms entered with the first K chunk
+        if (kEpi == EPI_SCREEN) {
+          // coarse (hi*hi only) screening: L = acc*c + |y|^2(1 - 2^-21) - 1.05*2^-9 |x||y| is a lower
+          // bound of the fp32-grade value (the dropped cross terms are at most 2^-10(1+2^-11)|x||y| in
+          // the dot product, i.e. 2^-9.. after the factor 2; the rest of the margin covers fp32 rounding)
+          col_ny[et] = gj < p.n ? sqrtf(tv) * (1.05f / 512.f) : 0.f;
+          if (gj < p.n) tv = tv - tv * (1.f / 2097152.f);
+        }
         col_tb[et] = tv;
       }
       ptx::bar_sync(1, 32 * TC_EPI_WARPS);
@@ -426,20 +452,25 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // the 4 tile rows this thread owns: 32q + quad + 8j, j = 0..3  (j = 2*rh + (0|1))
         const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;
         uint64_t ta2[4];
-        float thr[4];  // EPI_MINLOC: value of the row's current global best (an upper bound: keys only decrease)
+        float thr[4];  // arg-min modes: the row's current best distance (an upper bound: keys only decrease)
+        float xnr[4];  // arg-min modes: the row term |x_i|^2 (cosine family: 1)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float rv = 0.f;
           thr[j]   = __int_as_float(0xff800000);  // -inf: rows outside the matrix never trigger
+          xnr[j]   = 0.f;
           if (row0 + 8 * j < p.m) {
-            if (kEpi == EPI_STORE && p.acc_mode < 2) rv = __ldg(&p.xt[row0 + 8 * j]);
+            if (kEpi != EPI_STORE || p.acc_mode < 2) rv = __ldg(&p.xt[row0 + 8 * j]);
+            xnr[j] = rv;
             if (kEpi == EPI_MINLOC) {
               const long long ck = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
               const int sb       = static_cast<int>(ck >> 32);
-              thr[j]             = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);  // +max key -> NaN-free +inf-ish
+              thr[j]             = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
               if (ck == 0x7FFFFFFFFFFFFFFFll) thr[j] = __int_as_float(0x7f800000);
             }
+            if (kEpi == EPI_SCREEN) thr[j] = __ldg(&p.thr[row0 + 8 * j]);
           }
+          if (kEpi == EPI_SCREEN) rv = -sqrtf(rv);  // row factor of the screening margin
           ta2[j] = pk(rv, rv);
         }
         const bool rows_in = static_cast<int64_t>(mt) * TC_BM + q * 32 + 31 < p.m;
@@ -482,12 +513,19 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (kEpi == EPI_STORE) {
               t0 = add2(ta2[2 * rh], tb2);
               t1 = add2(ta2[2 * rh + 1], tb2);
-            } else {  // the row-constant |x_i|^2 does not change the arg-min: added once at the end
+            } else {  // the row-constant |x_i|^2 does not change the arg-min: added on the slow path only
               t0 = tb2;
               t1 = tb2;
             }
-            unpk(fma2(a0, cf2, t0), v[4 * i], v[4 * i + 1]);
-            unpk(fma2(a1, cf2, t1), v[4 * i + 2], v[4 * i + 3]);
+            uint64_t w0 = fma2(a0, cf2, t0), w1 = fma2(a1, cf2, t1);
+            if (kEpi == EPI_SCREEN) {  // lower bound: subtract the margin |x_i| * ny_j
+              const float2 ny  = *reinterpret_cast<const float2*>(&col_ny[cl0 + 8 * i]);
+              const uint64_t n2 = pk(ny.x, ny.y);
+              w0 = fma2(ta2[2 * rh], n2, w0);
+              w1 = fma2(ta2[2 * rh + 1], n2, w1);
+            }
+            unpk(w0, v[4 * i], v[4 * i + 1]);
+            unpk(w1, v[4 * i + 2], v[4 * i + 3]);
           }
           if (f < 3) {  // r / rc are dead: fetch the next fragment while this one is stored / reduced
             const int nf       = f + 1;
@@ -591,20 +629,42 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               m1          = min3(m1, v[28 + o], v[28 + o + 1]);
               const float mn = fminf(min3(m0, m1, m2), m3);
               const int j    = 2 * rh + rr;
-              // (+inf marks columns beyond n: never a candidate)
-              const bool cand = mn <= thr[j] && mn < __int_as_float(0x7f800000);
+              // (+inf marks columns beyond n: never a candidate).  Keys hold the full distance
+              // |x|^2 + v, so the row term is added for the comparison -- one FADD per row here
+              // instead of one per element
+              const float inf = __int_as_float(0x7f800000);
+              const bool cand = (mn + xnr[j]) <= thr[j] && mn < inf;
               if (__any_sync(0xffffffffu, cand)) {
                 if (cand) {
-                  int cbest = 0;
+                  if (kEpi == EPI_MINLOC) {
+                    int cbest = 0;
 #pragma unroll
-                  for (int i = 7; i >= 0; --i) {
-                    if (v[4 * i + o + 1] == mn) cbest = 8 * i + 1;
-                    if (v[4 * i + o] == mn) cbest = 8 * i;
+                    for (int i = 7; i >= 0; --i) {
+                      if (v[4 * i + o + 1] == mn) cbest = 8 * i + 1;
+                      if (v[4 * i + o] == mn) cbest = 8 * i;
+                    }
+                    const float dv      = mn + xnr[j];
+                    const long long gj  = static_cast<long long>(n_blk) * TC_BN + cl0 + cbest + p.idx_offset;
+                    const long long key = (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
+                    atomicMin(&p.keys[row0 + 8 * j], key);
+                    thr[j] = dv;
+                  } else {
+                    // every column whose lower bound reaches the row's upper bound goes to the exact pass
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                      for (int e = 0; e < 2; ++e) {
+                        const float lv = v[4 * i + o + e];
+                        if ((lv + xnr[j]) <= thr[j] && lv < inf) {
+                          const unsigned slot = atomicAdd(p.cand_cnt, 1u);
+                          if (slot < p.cand_cap)
+                            p.cand[slot] = make_int2(static_cast<int>(row0 + 8 * j),
+                                                     n_blk * TC_BN + cl0 + 8 * i + e);
+                          else
+                            *p.overflow = 1u;
+                        }
+                      }
                   }
-                  const long long gj  = static_cast<long long>(n_blk) * TC_BN + cl0 + cbest + p.idx_offset;
-                  const long long key = (static_cast<long long>(ordered_bits(mn)) << 32) | (gj & 0xFFFFFFFFll);
-                  atomicMin(&p.keys[row0 + 8 * j], key);
-                  thr[j] = mn;
                 }
               }
             }
@@ -640,10 +700,9 @@ struct KvpIF {
   float value;
 };
 
-// packed key -> raft::KeyValuePair<int,float>{argmin, min distance}; adds the row-constant
-// |x_i|^2 that the pair loop leaves out, clamps at 0, optional sqrt.
-__global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const float* xt,
-                                       int64_t m, int do_sqrt, int merge_existing)
+// packed key -> raft::KeyValuePair<int,float>{argmin, min distance}: clamp at 0, optional sqrt.
+__global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, int64_t m, int do_sqrt,
+                                       int merge_existing)
 {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -651,7 +710,7 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const 
   int s               = static_cast<int>(key >> 32);
   int bits            = s < 0 ? (s ^ 0x7FFFFFFF) : s;
   float v             = __int_as_float(bits);
-  float d             = fmaxf(xt[i] + v, 0.f);
+  float d             = fmaxf(v, 0.f);
   if (do_sqrt) d = sqrtf(d);
   KvpIF o;
   o.key   = static_cast<int>(key & 0xFFFFFFFFll);
@@ -666,6 +725,64 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, const 
     if ((e.value < o.value) || (e.value == o.value && e.key < o.key)) o = e;
   }
   out[i] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Screened fusedL2NN (k <= 128, large n): an exact pass over every 8th y block gives each row an
+// upper bound of its minimum; a coarse hi*hi-only pass over the other blocks (1 tensor product
+// instead of 3) keeps only the columns whose rigorous LOWER bound reaches that upper bound; those
+// few are re-evaluated exactly, straight from the fp32 inputs (sum (x-y)^2), together with the
+// incumbent, so every finalist is measured with the same arithmetic.
+
+// after the exact sub-sampled pass: thr = incumbent distance, incumbent -> candidate, keys reset
+__global__ void nn_seed_kernel(long long* keys, float* thr, int2* cand, unsigned* cnt, unsigned* overflow, int64_t m,
+                               int64_t n, int64_t idx_offset)
+{
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0) { *cnt = static_cast<unsigned>(m); *overflow = 0u; }
+  if (i >= m) return;
+  const long long key = keys[i];
+  float t             = __int_as_float(0x7f800000);
+  int2 c              = make_int2(-1, -1);
+  if (key != 0x7FFFFFFFFFFFFFFFll) {
+    const int sb = static_cast<int>(key >> 32);
+    t            = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
+    const long long j = (key & 0xFFFFFFFFll) - idx_offset;
+    if (j >= 0 && j < n) {  // incumbent of THIS shard: re-measured with the exact arithmetic below
+      c       = make_int2(static_cast<int>(i), static_cast<int>(j));
+      keys[i] = 0x7FFFFFFFFFFFFFFFll;
+    }                        // else: a key merged in from another shard stays as it is
+  }
+  thr[i]  = t;
+  cand[i] = c;
+}
+
+// one warp per candidate: d = sum (x_i - y_j)^2 in fp32 from the original inputs
+__global__ void __launch_bounds__(256) nn_exact_kernel(long long* keys, const int2* cand, const unsigned* cnt,
+                                                       unsigned cap, const float* x, int64_t ldx, const float* y,
+                                                       int64_t ldy, int k, int64_t idx_offset)
+{
+  const int lane       = threadIdx.x & 31;
+  const unsigned total = min(*cnt, cap);
+  const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
+  for (unsigned c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < total; c += nwarp) {
+    const int2 ij = cand[c];
+    if (ij.x < 0) continue;
+    const float* xr = x + static_cast<int64_t>(ij.x) * ldx;
+    const float* yr = y + static_cast<int64_t>(ij.y) * ldy;
+    float acc       = 0.f;
+    for (int t = lane; t < k; t += 32) {
+      const float d = __ldg(xr + t) - __ldg(yr + t);
+      acc           = fmaf(d, d, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const long long gj  = static_cast<long long>(ij.y) + idx_offset;
+      const long long key = (static_cast<long long>(ordered_bits(acc)) << 32) | (gj & 0xFFFFFFFFll);
+      atomicMin(&keys[ij.x], key);
+    }
+  }
 }
 
 }  // namespace b2d
