@@ -92,7 +92,7 @@ struct TcWorkspace {
   unsigned* gmax;  // [2]
   float* coef;     // [1]
   unsigned* has_lo;  // [1]
-  float* thr;        // [m]    screened NN: per-row upper bound
+  float2* aux;       // [m]    screened NN: per-row (bound - |x|^2, -|x|)
   int2* cand;        // [cap]  screened NN: candidate list
   unsigned* cand_cnt;  // [1] (+ overflow flag right behind it)
   unsigned cand_cap;
@@ -120,7 +120,7 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   // screened fusedL2NN scratch: thresholds, counters, candidate list (64 per row: ~50 expected on
   // clustered data; overflow falls back to the exact pass on the device, never to a wrong answer)
   w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(64 * m + (1 << 16), 0x7fffffff)) : 0u;
-  w.thr      = reinterpret_cast<float*>(c + take(with_keys ? static_cast<size_t>(m) * 4 : 0));
+  w.aux      = reinterpret_cast<float2*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
   w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 16 : 0));
   w.cand     = reinterpret_cast<int2*>(c + take(static_cast<size_t>(w.cand_cap) * 8));
   w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
@@ -186,7 +186,7 @@ static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorM
   // the attribute is per device and per function: cheap, set on every launch
   B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost, kTma>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES)));
-  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, p);
+  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, tc_threads(kEpi), TC_SMEM_BYTES, s>>>(ma, mb, md, p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -475,7 +475,8 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
   const int nkb = static_cast<int>((k + 31) / 32);
   static const bool screen_off = getenv("B2D_NN_SCREEN") != nullptr && atoi(getenv("B2D_NN_SCREEN")) == 0;
-  const bool screen = mode == PREP_L2 && nkb <= TC_MAX_RES_KB && n >= 16384 && !screen_off;
+  // (k <= 64: the exact kernel is already epilogue-bound, screening would not pay)
+  const bool screen = mode == PREP_L2 && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && !screen_off;
   if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 
   // Screened search (see expanded_tc.cuh): exact on every 8th y block -> bound; coarse 1-product pass
@@ -486,10 +487,10 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
   unsigned* overflow = w.cand_cnt + 1;
-  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.thr, w.cand,
-                                                                         w.cand_cnt, overflow, m, n, idx_offset);
+  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
+                                                                         w.cand, w.cand_cnt, overflow, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
-  p.sel_mode = 2; p.thr = w.thr; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
+  p.sel_mode = 2; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
   p.overflow = overflow; p.force_no_lo = 1;
   rc = launch_tc(s, w, p, k, EPI_SCREEN, POST_NONE);
   if (rc) return rc;

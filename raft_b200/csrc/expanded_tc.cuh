@@ -63,6 +63,9 @@ constexpr int TC_STAGES_STR  = 4;            // A+B stages (48 KB) when both ope
 constexpr int TC_MAX_STAGES  = 6;
 constexpr int TC_EPI_WARPS   = 8;
 constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
+// EPI_SCREEN runs two sets of epilogue warps, one per TMEM accumulator stage (even / odd tiles): its
+// MMA work is a third of the exact kernel's, so the latency-bound epilogue needs twice the warps
+__host__ __device__ constexpr int tc_threads(int epi) { return 64 + 32 * TC_EPI_WARPS * (epi == 2 ? 2 : 1); }
 
 enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1, EPI_SCREEN = 2 };
 enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
@@ -89,7 +92,7 @@ struct TcParams {
   // EPI_MINLOC / EPI_SCREEN
   long long* keys;        // [m] packed (ordered bits of the distance << 32 | index)
   int64_t idx_offset;
-  const float* thr;       // EPI_SCREEN: [m] upper bound of the row's true minimum distance
+  const float2* aux;      // EPI_SCREEN: [m] (upper bound of the row's minimum minus |x_i|^2, -|x_i|)
   int2* cand;             // EPI_SCREEN: candidate (row, column) list
   unsigned* cand_cnt;     //             its fill counter ...
   unsigned cand_cap;      //             ... capacity ...
@@ -161,7 +164,7 @@ __device__ __forceinline__ float min3(float a, float b, float c)
 }
 
 template <bool kResident, int kEpi, int kPost, bool kTma>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(kEpi), 1)
 expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_d, const TcParams p)
 {
@@ -331,12 +334,18 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else {
     // ================================ epilogue warps ===============================
+    constexpr int kSets = kEpi == EPI_SCREEN ? 2 : 1;
     const int q    = warp & 3;          // TMEM lane quarter this warp may read: tile rows [32q, 32q+32)
-    const int g    = (warp - 2) >> 2;   // column half of the tile this warp drains: [128g, 128g+128)
-    const int et   = threadIdx.x - 64;  // 0..255
+    const int set  = (warp - 2) >> 3;   // which accumulator stage (tile parity) this warp drains when kSets == 2
+    const int g    = ((warp - 2) & 7) >> 2;  // column half of the tile this warp drains: [128g, 128g+128)
+    const int et   = threadIdx.x - 64;  // 0..255 (fills the per-column terms)
     const int quad = lane >> 2;         // fragment row inside a 16-row group (and +8)
     const int tq   = lane & 3;          // fragment column pair inside an 8-column group
     uint32_t t_it  = 0;
+    float2 aux_cur[4], aux_nxt[4];
+    int64_t pre_tag = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j] = make_float2(0.f, 0.f);
     const float cf     = __ldg(p.coef);
     const bool add_cross = !kResident && !p.force_no_lo && __ldg(p.has_lo) != 0u;  // streaming layout keeps cross terms apart
     const uint64_t pol_st = ptx::policy_evict_first();
@@ -347,8 +356,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
       // per-column epilogue terms of this y block (shared by every tile of the item)
-      ptx::bar_sync(1, 32 * TC_EPI_WARPS);
-      {
+      ptx::bar_sync(1, 32 * TC_EPI_WARPS * kSets);
+      if (et < TC_BN) {
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
         float tv = kEpi != EPI_STORE ? __int_as_float(0x7f800000) : 0.f;  // +inf: never the arg-min
         if (gj < p.n) tv = __ldg(&p.yt[gj]);
@@ -362,11 +371,12 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         col_tb[et] = tv;
       }
-      ptx::bar_sync(1, 32 * TC_EPI_WARPS);
+      ptx::bar_sync(1, 32 * TC_EPI_WARPS * kSets);
       const int64_t col0 = static_cast<int64_t>(n_blk) * TC_BN + g * 128;  // first global column of this warp
       const bool cols_in = col0 + 127 < p.n;
 
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
+        if (kSets == 2 && static_cast<int>(t_it & 1) != set) continue;  // the other warp set owns this tile
         if (kTma) {
           // ---------------- EPI_STORE through shared memory + TMA tensor store ----------------
           uint32_t tb_idx, tph;
@@ -379,8 +389,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           // k <= 96 leaves the 4th y slab unused: a second staging block per warp lets the TMA store
           // of chunk c overlap the staging of chunk c+1
           const bool dbuf     = kResident && nkb <= 3;
-          float* stg_a        = stg + (warp - 2) * 1024;
-          float* stg_b        = dbuf ? reinterpret_cast<float*>(b_base + 3 * TC_B_BYTES) + (warp - 2) * 1024 : stg_a;
+          float* stg_a        = stg + ((warp - 2) & 7) * 1024;
+          float* stg_b        = dbuf ? reinterpret_cast<float*>(b_base + 3 * TC_B_BYTES) + ((warp - 2) & 7) * 1024 : stg_a;
           ptx::mbar_wait(&tfull[tb_idx], tph);
           ptx::tc_fence_after();
           const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -452,26 +462,50 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // the 4 tile rows this thread owns: 32q + quad + 8j, j = 0..3  (j = 2*rh + (0|1))
         const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;
         uint64_t ta2[4];
-        float thr[4];  // arg-min modes: the row's current best distance (an upper bound: keys only decrease)
-        float xnr[4];  // arg-min modes: the row term |x_i|^2 (cosine family: 1)
+        float thr[4];  // arg-min modes: the row's current best (an upper bound: keys only decrease)
+        float xnr[4];  // EPI_MINLOC: the row term |x_i|^2 (cosine family: 1)
+        if (kEpi == EPI_SCREEN) {
+          // (bound, -|x_i|) pairs are fetched one of this warp's tiles ahead: no global-load latency here
+          const int64_t tag = item * 65536 + mt;
+          if (pre_tag != tag) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float rv = 0.f;
-          thr[j]   = __int_as_float(0xff800000);  // -inf: rows outside the matrix never trigger
-          xnr[j]   = 0.f;
-          if (row0 + 8 * j < p.m) {
-            if (kEpi != EPI_STORE || p.acc_mode < 2) rv = __ldg(&p.xt[row0 + 8 * j]);
-            xnr[j] = rv;
-            if (kEpi == EPI_MINLOC) {
-              const long long ck = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
-              const int sb       = static_cast<int>(ck >> 32);
-              thr[j]             = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
-              if (ck == 0x7FFFFFFFFFFFFFFFll) thr[j] = __int_as_float(0x7f800000);
-            }
-            if (kEpi == EPI_SCREEN) thr[j] = __ldg(&p.thr[row0 + 8 * j]);
+            for (int j = 0; j < 4; ++j)
+              aux_cur[j] = row0 + 8 * j < p.m ? __ldg(&p.aux[row0 + 8 * j]) : make_float2(__int_as_float(0xff800000), 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
           }
-          if (kEpi == EPI_SCREEN) rv = -sqrtf(rv);  // row factor of the screening margin
-          ta2[j] = pk(rv, rv);
+          if (mt + kSets < mt1) {
+            pre_tag = item * 65536 + mt + kSets;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              aux_nxt[j] = row0 + kSets * TC_BM + 8 * j < p.m ? __ldg(&p.aux[row0 + kSets * TC_BM + 8 * j])
+                                                              : make_float2(__int_as_float(0xff800000), 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            thr[j] = aux_cur[j].x;
+            xnr[j] = 0.f;
+            ta2[j] = pk(aux_cur[j].y, aux_cur[j].y);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float rv = 0.f;
+            thr[j]   = __int_as_float(0xff800000);  // -inf: rows outside the matrix never trigger
+            xnr[j]   = 0.f;
+            if (row0 + 8 * j < p.m) {
+              if (kEpi != EPI_STORE || p.acc_mode < 2) rv = __ldg(&p.xt[row0 + 8 * j]);
+              xnr[j] = rv;
+              if (kEpi == EPI_MINLOC) {
+                const long long ck = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
+                const int sb       = static_cast<int>(ck >> 32);
+                thr[j]             = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
+                if (ck == 0x7FFFFFFFFFFFFFFFll) thr[j] = __int_as_float(0x7f800000);
+              }
+            }
+            ta2[j] = pk(rv, rv);
+          }
         }
         const bool rows_in = static_cast<int64_t>(mt) * TC_BM + q * 32 + 31 < p.m;
 
@@ -735,8 +769,8 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, int64_
 // incumbent, so every finalist is measured with the same arithmetic.
 
 // after the exact sub-sampled pass: thr = incumbent distance, incumbent -> candidate, keys reset
-__global__ void nn_seed_kernel(long long* keys, float* thr, int2* cand, unsigned* cnt, unsigned* overflow, int64_t m,
-                               int64_t n, int64_t idx_offset)
+__global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, int2* cand, unsigned* cnt,
+                               unsigned* overflow, int64_t m, int64_t n, int64_t idx_offset)
 {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i == 0) { *cnt = static_cast<unsigned>(m); *overflow = 0u; }
@@ -753,7 +787,9 @@ __global__ void nn_seed_kernel(long long* keys, float* thr, int2* cand, unsigned
       keys[i] = 0x7FFFFFFFFFFFFFFFll;
     }                        // else: a key merged in from another shard stays as it is
   }
-  thr[i]  = t;
+  // screening compares v = d - |x|^2 with (bound - |x|^2), rounded up so that it stays an upper bound
+  const float xn = xt[i];
+  aux[i]  = make_float2((t - xn) + (t + xn) * (1.f / 2097152.f), -sqrtf(xn));
   cand[i] = c;
 }
 
