@@ -10,6 +10,7 @@
 
 #include "../../include/raft_b200.h"
 #include "expanded_tc.cuh"
+#include "screen_tc.cuh"
 #include "prep.cuh"
 #include "unexpanded_simt.cuh"
 
@@ -54,8 +55,9 @@ static EncodeTiledFn get_encode()
 }
 
 // packed operand [rows][nkb*64] fp16, box = 64 x box_rows, SWIZZLE_128B
+// (hi_only: boxes of the 32 hi halves of a k-block, 64 B rows, SWIZZLE_64B -- the coarse screening pass)
 static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int nkb, int box_rows,
-                            int kb0 = 0, int nkb_total = 0)
+                            int kb0 = 0, int nkb_total = 0, bool hi_only = false)
 {
   if (nkb_total == 0) nkb_total = nkb;
   base = static_cast<const char*>(base) + static_cast<size_t>(kb0) * 128;  // K chunk [kb0, kb0 + nkb) of every row
@@ -63,10 +65,10 @@ static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, in
   if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[2]    = {static_cast<cuuint64_t>(nkb) * 64, static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(nkb_total) * 128};
-  cuuint32_t box[2]     = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2]     = {hi_only ? 32u : 64u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2]    = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, hi_only ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return B2D_OK;
@@ -186,7 +188,7 @@ static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorM
   // the attribute is per device and per function: cheap, set on every launch
   B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost, kTma>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES)));
-  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, tc_threads(kEpi), TC_SMEM_BYTES, s>>>(ma, mb, md, p);
+  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -241,10 +243,6 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
     return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
                     : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
-  if (epi == EPI_SCREEN) {
-    if (!resident) return fail(B2D_ERR_UNSUPPORTED, "internal: screening needs the resident kernel");
-    return launch_tc_inst<true, EPI_SCREEN, POST_NONE, false>(s, ma, mb, md, p, grid);
-  }
   // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
   // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
   // unaligned outputs take the direct register->global path
@@ -258,6 +256,48 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   }
   return resident ? launch_tc_store<true, false>(s, ma, mb, md, p, grid, post)
                   : launch_tc_store<false, false>(s, ma, mb, md, p, grid, post);
+}
+
+// coarse screening pass of the screened fusedL2NN (screen_tc.cuh) over the y blocks with index % sel_s != 0
+static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_t n, int64_t k, int sel_s,
+                         unsigned* overflow)
+{
+  int sms = 0, cc = 0;
+  int rc  = device_sms(&sms, &cc);
+  if (rc) return rc;
+  if (cc != 10) return fail(B2D_ERR_CUDA, "raft_b200 requires an sm_100 (B200) device; found cc major " + std::to_string(cc));
+  ScreenParams p;
+  memset(&p, 0, sizeof(p));
+  p.m = m; p.n = n;
+  p.nkb     = static_cast<int>((k + 31) / 32);
+  if (p.nkb > SC_MAX_KB) return fail(B2D_ERR_UNSUPPORTED, "internal: screening needs k <= 128");
+  p.n_stages = static_cast<int>(std::min<size_t>(SC_MAX_STAGES, SC_A_RING / (static_cast<size_t>(p.nkb) * SC_A_KB_BYTES)));
+  p.tiles_m = static_cast<int>((m + TC_BM - 1) / TC_BM);
+  const int tiles_n = static_cast<int>((n + TC_BN - 1) / TC_BN);
+  p.sel_mode = 2; p.sel_s = sel_s;
+  p.tiles_sel = tiles_n - (tiles_n + sel_s - 1) / sel_s;
+  // long runs of x tiles per y block: the y block load is not overlapped with the previous item
+  int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_sel;
+  int64_t chunk = total / (static_cast<int64_t>(sms) * 4);
+  chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, 128));
+  chunk = std::min<int64_t>(chunk, p.tiles_m);
+  p.chunk    = static_cast<int>(chunk);
+  p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
+  p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
+  p.yt = w.yt; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
+  p.overflow = overflow;
+  if (p.n_items == 0) return B2D_OK;
+  CUtensorMap ma, mb;
+  rc = make_operand_map(&ma, w.xop, m, p.nkb, TC_BM, 0, 0, true);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, w.yop, n, p.nkb, TC_BN, 0, 0, true);
+  if (rc) return rc;
+  const int grid = static_cast<int>(p.n_items < sms ? p.n_items : sms);
+  B2D_CUDA(cudaFuncSetAttribute(screen_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(SC_SMEM_BYTES)));
+  screen_tc_kernel<<<grid, SC_THREADS, SC_SMEM_BYTES, s>>>(ma, mb, p);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
 }
 
 // fp32 row-major matrix [rows][k] with row pitch ld: box = 32 floats x 128 rows, SWIZZLE_128B
@@ -482,7 +522,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   // Screened search (see expanded_tc.cuh): exact on every 8th y block -> bound; coarse 1-product pass
   // over the rest -> candidates; exact re-evaluation of the candidates; exact fallback only if the
   // candidate list overflowed (decided on the device: no host round trip).
-  constexpr int kSel = 8;
+  constexpr int kSel = 32;
   p.sel_mode = 1; p.sel_s = kSel;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
@@ -490,9 +530,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
                                                                          w.cand, w.cand_cnt, overflow, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
-  p.sel_mode = 2; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
-  p.overflow = overflow; p.force_no_lo = 1;
-  rc = launch_tc(s, w, p, k, EPI_SCREEN, POST_NONE);
+  rc = launch_screen(s, w, m, n, k, kSel, overflow);
   if (rc) return rc;
   int sms = 0, cc = 0;
   rc = device_sms(&sms, &cc);
@@ -500,7 +538,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
                                           ldy, static_cast<int>(k), idx_offset);
   B2D_CUDA(cudaGetLastError());
-  p.force_no_lo = 0; p.run_flag = overflow;  // runs only if candidates were dropped
+  p.sel_mode = 2; p.run_flag = overflow;  // the other blocks, exactly: runs only if candidates were dropped
   return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 }
 

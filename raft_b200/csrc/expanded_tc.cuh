@@ -63,11 +63,8 @@ constexpr int TC_STAGES_STR  = 4;            // A+B stages (48 KB) when both ope
 constexpr int TC_MAX_STAGES  = 6;
 constexpr int TC_EPI_WARPS   = 8;
 constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
-// EPI_SCREEN runs two sets of epilogue warps, one per TMEM accumulator stage (even / odd tiles): its
-// MMA work is a third of the exact kernel's, so the latency-bound epilogue needs twice the warps
-__host__ __device__ constexpr int tc_threads(int epi) { return 64 + 32 * TC_EPI_WARPS * (epi == 2 ? 2 : 1); }
 
-enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1, EPI_SCREEN = 2 };
+enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1 };
 enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
 
 struct TcParams {
@@ -89,21 +86,15 @@ struct TcParams {
   int diag_zero;          // x and y alias: force d(i,i) = 0 (reference: CHANGELOG.md:1057,1213)
   int pair_ok;            // dist 8-byte aligned and ldd even -> st.v2
   int acc_mode;           // K-chunked accumulation: 0 single pass, 1 first chunk (raw store), 2 middle (+=), 3 last (+=, post)
-  // EPI_MINLOC / EPI_SCREEN
+  // EPI_MINLOC
   long long* keys;        // [m] packed (ordered bits of the distance << 32 | index)
   int64_t idx_offset;
-  const float2* aux;      // EPI_SCREEN: [m] (upper bound of the row's minimum minus |x_i|^2, -|x_i|)
-  int2* cand;             // EPI_SCREEN: candidate (row, column) list
-  unsigned* cand_cnt;     //             its fill counter ...
-  unsigned cand_cap;      //             ... capacity ...
-  unsigned* overflow;     //             ... and overflow flag (then the exact pass re-runs)
   const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
-  int force_no_lo;        // coarse pass: hi*hi only
 };
 
 constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES_RES * TC_A_BYTES;  // 224 KB
 static_assert((size_t)TC_STAGES_STR * (TC_A_BYTES + TC_B_BYTES) <= TC_SMEM_OPERANDS, "streaming carve fits");
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + 2 * TC_BN * 4 + 256;
+constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_BN * 4 + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
 
 // index of the s-th selected y block (see TcParams::sel_mode)
@@ -164,7 +155,7 @@ __device__ __forceinline__ float min3(float a, float b, float c)
 }
 
 template <bool kResident, int kEpi, int kPost, bool kTma>
-__global__ void __launch_bounds__(tc_threads(kEpi), 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_d, const TcParams p)
 {
@@ -181,8 +172,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES_STR * TC_B_BYTES);
   float* stg      = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS - TC_EPI_WARPS * 4096);  // kTma only
   float* col_tb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);  // [256] t_y of this y block
-  float* col_ny   = col_tb + TC_BN;                                     // [256] EPI_SCREEN: scaled |y_j|
-  uint64_t* bars  = reinterpret_cast<uint64_t*>(col_ny + TC_BN);
+  uint64_t* bars  = reinterpret_cast<uint64_t*>(col_tb + TC_BN);
   uint64_t* afull = bars;                       // [TC_MAX_STAGES]
   uint64_t* aempty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
   uint64_t* bfull = bars + 2 * TC_MAX_STAGES;   // [TC_MAX_RES_KB]
@@ -250,7 +240,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // descriptor start-address units are 16 B; inside the 128-B swizzled row of a k-block:
     //   hi k[0,16) +0, hi k[16,32) +2, lo k[0,16) +4, lo k[16,32) +6
     uint32_t a_it = 0, t_it = 0, it_local = 0;
-    const bool has_lo = !p.force_no_lo && __ldg(p.has_lo) != 0u;
+    const bool has_lo = __ldg(p.has_lo) != 0u;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
       const int ch  = static_cast<int>(item / p.tiles_sel);
       const int mt0 = ch * p.chunk;
@@ -334,20 +324,14 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else {
     // ================================ epilogue warps ===============================
-    constexpr int kSets = kEpi == EPI_SCREEN ? 2 : 1;
     const int q    = warp & 3;          // TMEM lane quarter this warp may read: tile rows [32q, 32q+32)
-    const int set  = (warp - 2) >> 3;   // which accumulator stage (tile parity) this warp drains when kSets == 2
-    const int g    = ((warp - 2) & 7) >> 2;  // column half of the tile this warp drains: [128g, 128g+128)
+    const int g    = (warp - 2) >> 2;   // column half of the tile this warp drains: [128g, 128g+128)
     const int et   = threadIdx.x - 64;  // 0..255 (fills the per-column terms)
     const int quad = lane >> 2;         // fragment row inside a 16-row group (and +8)
     const int tq   = lane & 3;          // fragment column pair inside an 8-column group
     uint32_t t_it  = 0;
-    float2 aux_cur[4], aux_nxt[4];
-    int64_t pre_tag = -1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j] = make_float2(0.f, 0.f);
     const float cf     = __ldg(p.coef);
-    const bool add_cross = !kResident && !p.force_no_lo && __ldg(p.has_lo) != 0u;  // streaming layout keeps cross terms apart
+    const bool add_cross = !kResident && __ldg(p.has_lo) != 0u;  // streaming layout keeps cross terms apart
     const uint64_t pol_st = ptx::policy_evict_first();
     const uint64_t cf2 = pk(cf, cf);
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -356,27 +340,19 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
       // per-column epilogue terms of this y block (shared by every tile of the item)
-      ptx::bar_sync(1, 32 * TC_EPI_WARPS * kSets);
+      ptx::bar_sync(1, 32 * TC_EPI_WARPS);
       if (et < TC_BN) {
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
         float tv = kEpi != EPI_STORE ? __int_as_float(0x7f800000) : 0.f;  // +inf: never the arg-min
         if (gj < p.n) tv = __ldg(&p.yt[gj]);
         if (kEpi == EPI_STORE && p.acc_mode >= 2) tv = 0.f;  // the t terms entered with the first K chunk
-        if (kEpi == EPI_SCREEN) {
-          // coarse (hi*hi only) screening: L = acc*c + |y|^2(1 - 2^-21) - 1.05*2^-9 |x||y| is a lower
-          // bound of the fp32-grade value (the dropped cross terms are at most 2^-10(1+2^-11)|x||y| in
-          // the dot product, i.e. 2^-9.. after the factor 2; the rest of the margin covers fp32 rounding)
-          col_ny[et] = gj < p.n ? sqrtf(tv) * (1.05f / 512.f) : 0.f;
-          if (gj < p.n) tv = tv - tv * (1.f / 2097152.f);
-        }
         col_tb[et] = tv;
       }
-      ptx::bar_sync(1, 32 * TC_EPI_WARPS * kSets);
+      ptx::bar_sync(1, 32 * TC_EPI_WARPS);
       const int64_t col0 = static_cast<int64_t>(n_blk) * TC_BN + g * 128;  // first global column of this warp
       const bool cols_in = col0 + 127 < p.n;
 
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
-        if (kSets == 2 && static_cast<int>(t_it & 1) != set) continue;  // the other warp set owns this tile
         if (kTma) {
           // ---------------- EPI_STORE through shared memory + TMA tensor store ----------------
           uint32_t tb_idx, tph;
@@ -464,31 +440,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint64_t ta2[4];
         float thr[4];  // arg-min modes: the row's current best (an upper bound: keys only decrease)
         float xnr[4];  // EPI_MINLOC: the row term |x_i|^2 (cosine family: 1)
-        if (kEpi == EPI_SCREEN) {
-          // (bound, -|x_i|) pairs are fetched one of this warp's tiles ahead: no global-load latency here
-          const int64_t tag = item * 65536 + mt;
-          if (pre_tag != tag) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              aux_cur[j] = row0 + 8 * j < p.m ? __ldg(&p.aux[row0 + 8 * j]) : make_float2(__int_as_float(0xff800000), 0.f);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) aux_cur[j] = aux_nxt[j];
-          }
-          if (mt + kSets < mt1) {
-            pre_tag = item * 65536 + mt + kSets;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              aux_nxt[j] = row0 + kSets * TC_BM + 8 * j < p.m ? __ldg(&p.aux[row0 + kSets * TC_BM + 8 * j])
-                                                              : make_float2(__int_as_float(0xff800000), 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            thr[j] = aux_cur[j].x;
-            xnr[j] = 0.f;
-            ta2[j] = pk(aux_cur[j].y, aux_cur[j].y);
-          }
-        } else {
+        {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float rv = 0.f;
@@ -552,12 +504,6 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               t1 = tb2;
             }
             uint64_t w0 = fma2(a0, cf2, t0), w1 = fma2(a1, cf2, t1);
-            if (kEpi == EPI_SCREEN) {  // lower bound: subtract the margin |x_i| * ny_j
-              const float2 ny  = *reinterpret_cast<const float2*>(&col_ny[cl0 + 8 * i]);
-              const uint64_t n2 = pk(ny.x, ny.y);
-              w0 = fma2(ta2[2 * rh], n2, w0);
-              w1 = fma2(ta2[2 * rh + 1], n2, w1);
-            }
             unpk(w0, v[4 * i], v[4 * i + 1]);
             unpk(w1, v[4 * i + 2], v[4 * i + 3]);
           }
@@ -682,22 +628,6 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     const long long key = (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
                     atomicMin(&p.keys[row0 + 8 * j], key);
                     thr[j] = dv;
-                  } else {
-                    // every column whose lower bound reaches the row's upper bound goes to the exact pass
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                      for (int e = 0; e < 2; ++e) {
-                        const float lv = v[4 * i + o + e];
-                        if ((lv + xnr[j]) <= thr[j] && lv < inf) {
-                          const unsigned slot = atomicAdd(p.cand_cnt, 1u);
-                          if (slot < p.cand_cap)
-                            p.cand[slot] = make_int2(static_cast<int>(row0 + 8 * j),
-                                                     n_blk * TC_BN + cl0 + 8 * i + e);
-                          else
-                            *p.overflow = 1u;
-                        }
-                      }
                   }
                 }
               }
@@ -762,11 +692,11 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Screened fusedL2NN (k <= 128, large n): an exact pass over every 8th y block gives each row an
-// upper bound of its minimum; a coarse hi*hi-only pass over the other blocks (1 tensor product
-// instead of 3) keeps only the columns whose rigorous LOWER bound reaches that upper bound; those
-// few are re-evaluated exactly, straight from the fp32 inputs (sum (x-y)^2), together with the
-// incumbent, so every finalist is measured with the same arithmetic.
+// Screened fusedL2NN (64 < k <= 128, large n): an exact pass over every 32nd y block gives each row an
+// upper bound of its minimum; the coarse pass of screen_tc.cuh (1 tensor product instead of 3)
+// keeps only the columns whose rigorous LOWER bound reaches that upper bound; those few are
+// re-evaluated exactly, straight from the fp32 inputs (sum (x-y)^2), together with the incumbent,
+// so every finalist is measured with the same arithmetic.
 
 // after the exact sub-sampled pass: thr = incumbent distance, incumbent -> candidate, keys reset
 __global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, int2* cand, unsigned* cnt,

@@ -187,6 +187,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     : "r"(taddr)
     : "memory");
 }
+// Same shape, 16 columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
+{
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+      "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+      "=r"(r[14]), "=r"(r[15])
+    : "r"(taddr)
+    : "memory");
+}
 // TMEM -> registers, 16 lanes x 256 bits, x8: 16 rows x 64 fp32 columns per warp.  Fragment (the
 // m16n8 accumulator layout, repeated along columns): thread t holds, for i in [0,8):
 //   r[4i+0], r[4i+1] = row (t/4),     columns 8i + 2(t%4) + {0,1}
@@ -223,6 +235,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Same, SWIZZLE_64B with rows of 64 bytes (8-row groups of 512 B; layout type 4): used where only
+// half of a packed k-block is staged.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr)
+{
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
   return d;
 }
 

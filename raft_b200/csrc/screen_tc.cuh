@@ -1,0 +1,369 @@
+// K3b: coarse screening pass of the screened fusedL2NN (sm_100a, tcgen05).
+//
+// fused_nn_keys (api.cu) first runs the exact arg-min kernel on every S-th 256-row block of y, which
+// leaves each x row with an upper bound U_i of its minimum.  This kernel visits the other blocks with
+// ONE tensor product per k-block (hi*hi only: a third of the exact kernel's MMA work, half of its
+// operand bytes) and computes, per pair, a rigorous LOWER bound of the fp32-grade distance
+//     L_ij = acc_ij * c + |y_j|^2 (1 - 2^-21) - 1.05 * 2^-9 |x_i| max_j' |y_j'|     (j' over the y block)
+// (dropped cross terms: at most 2^-10 (1 + 2^-11) |x||y| in the dot product, i.e. 2^-9.. after the
+// factor 2; the remaining 5% of the margin and the 2^-21 |y|^2 cover the fp32 rounding of the
+// epilogue).  Only pairs with L_ij <= U_i can hold the minimum: they go to a candidate list that
+// nn_exact_kernel re-measures straight from the fp32 inputs.  The margin is a per-row constant
+// inside a y block, so it moves into the row's threshold and the element loop is one FFMA2 plus a
+// running FMNMX3.
+//
+// Every coarse value is also an UPPER bound of a real pair's distance (value + margin), so a row's
+// bound tightens (atomic min on aux[i].x) whenever one of its candidates is found: 2.3 candidates per
+// row on 1M x 1M x 96 Gaussian data instead of the 7.3 that a fixed 1/8 sample leaves, which is
+// what lets the exact pass sample only every 32nd block.
+//
+// A 128 x 256 tile is ~770 tensor cycles here (6 MMAs at k = 96) instead of 2300, so everything
+// around the tensor core had to shrink with it.  Measured with clock64 timelines per role
+// (1M x 1M x 96, cycles per tile): the first version re-used the exact kernel's roles and took 2300
+// -- the single MMA warp spent 740 issuing (tcgen05.mma issue blocks while the pipe's queue is full),
+// 810 + 690 in barrier polls and bookkeeping while the pipe idled, and the epilogue exposed one TMEM
+// load latency per fragment.  This kernel: 1150.  Isolation runs: operands + MMAs alone 1010,
+// epilogue alone 1100, synchronisation skeleton alone 620.
+//   operands   hi halves only: TMA boxes of 32 fp16 (64 B, SWIZZLE_64B) out of the packed
+//              [hi32|lo32] k-blocks; a stage is one whole x tile (nkb x 8 KB), 5-6 stages deep,
+//              one mbarrier round trip per TILE; the y block (nkb x 16 KB) is resident per item
+//   MMA        two issuer warps, one per TMEM accumulator stage (even / odd tiles): while one is
+//              blocked in issue the other has finished its polls, so the pipe stays fed.  All waits
+//              first, then one elected region queues every MMA of the tile and the commits
+//              (x stage free, accumulator full)
+//   epilogue   16 warps on every tile (32 rows x 64 columns each), thread == row
+//              (tcgen05.ld.32x32b, the fastest TMEM read shape: 403 vs 571 cycles per tile for
+//              16x256b, scripts/probes/tmem_probe.cu), software-pipelined over two 16-column register
+//              buffers so that the load of fragment f+1 overlaps the arithmetic of fragment f, no
+//              branches inside: per 32-column group one compare sets a bit of a hit mask.  A warp
+//              with a hit (1-2 % of the warp-tiles) reads those groups again, notes the candidate
+//              columns in a 64-bit mask, hands the accumulator back and only then takes the atomics
+//              (list append, bound update)
+#pragma once
+#include "expanded_tc.cuh"
+
+namespace b2d {
+
+constexpr int SC_A_KB_BYTES   = TC_BM * 64;  // one k-block of an x tile, hi halves: 128 rows x 64 B
+constexpr int SC_B_KB_BYTES   = TC_BN * 64;  // one k-block of the y block:          256 rows x 64 B
+constexpr int SC_MAX_KB       = 4;           // k <= 128
+constexpr int SC_MAX_STAGES   = 8;
+constexpr int SC_EPI_WARPS    = 16;
+#ifndef SC_SETS
+#define SC_SETS 1
+#endif
+constexpr int SC_CW           = 64 * SC_SETS;  // columns of a tile one epilogue warp drains
+constexpr int SC_MMA2_WARP    = 2 + SC_EPI_WARPS;  // second MMA issuer (the first is warp 1)
+constexpr int SC_THREADS      = 96 + 32 * SC_EPI_WARPS;
+constexpr size_t SC_A_RING    = 160 * 1024;
+constexpr size_t SC_SMEM_OPERANDS = (size_t)SC_MAX_KB * SC_B_KB_BYTES + SC_A_RING;  // 224 KB
+constexpr size_t SC_SMEM_BYTES    = SC_SMEM_OPERANDS + TC_BN * 4 + 32 + 256;
+static_assert(SC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
+
+struct ScreenParams {
+  int64_t m, n;
+  int nkb;                // k-blocks of 32 source columns (<= SC_MAX_KB)
+  int n_stages;           // x-tile stages in the ring (host: min(SC_MAX_STAGES, SC_A_RING / (nkb * 8 KB)))
+  int tiles_m, tiles_sel; // ceil(m/128); y blocks this launch visits
+  int sel_mode, sel_s;    // as TcParams
+  int chunk, chunks_m;    // m-tiles per work item
+  int64_t n_items;
+  const float* yt;        // [n] |y_j|^2
+  const float* coef;      // [1] -2 * 2^-(ex+ey)
+  float2* aux;            // [m] (U_i - |x_i|^2 rounded up, -|x_i|); the bound tightens as candidates are found
+  int2* cand;             // candidate (row, column) list ...
+  unsigned* cand_cnt;     // ... its fill counter ...
+  unsigned cand_cap;      // ... capacity ...
+  unsigned* overflow;     // ... and overflow flag (then the exact pass re-runs)
+};
+
+// 16 columns of this thread's row: lower bounds folded into four running minima (no branches: the
+// eight fragments of a tile overlap in the instruction stream)
+#define B2D_SCREEN_FRAGMENT(R, CBASE)                                                                   \
+  _Pragma("unroll") for (int c = 0; c < 16; c += 8)                                                     \
+  {                                                                                                     \
+    const float4 ta = *reinterpret_cast<const float4*>(&col_tb[(CBASE) + c]);                           \
+    const float4 tb = *reinterpret_cast<const float4*>(&col_tb[(CBASE) + c + 4]);                       \
+    float v0, v1, v2, v3, v4, v5, v6, v7;                                                               \
+    unpk(fma2(pk(R[c], R[c + 1]), cf2, pk(ta.x, ta.y)), v0, v1);                                        \
+    unpk(fma2(pk(R[c + 2], R[c + 3]), cf2, pk(ta.z, ta.w)), v2, v3);                                    \
+    unpk(fma2(pk(R[c + 4], R[c + 5]), cf2, pk(tb.x, tb.y)), v4, v5);                                    \
+    unpk(fma2(pk(R[c + 6], R[c + 7]), cf2, pk(tb.z, tb.w)), v6, v7);                                    \
+    m0 = min3(m0, v0, v1);                                                                              \
+    m1 = min3(m1, v2, v3);                                                                              \
+    m2 = min3(m2, v4, v5);                                                                              \
+    m3 = min3(m3, v6, v7);                                                                              \
+  }
+
+__global__ void __launch_bounds__(SC_THREADS, 1)
+screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ScreenParams p)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* b_base  = smem;
+  uint8_t* a_base  = smem + SC_MAX_KB * SC_B_KB_BYTES;
+  float* col_tb    = reinterpret_cast<float*>(smem + SC_SMEM_OPERANDS);  // [256] |y_j|^2 (1 - 2^-21), +inf beyond n
+  float* col_ny    = col_tb + TC_BN;                                     // [8] per-warp maxima of the margin factor
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(col_ny + 8);
+  uint64_t* afull  = bars;                      // [SC_MAX_STAGES]
+  uint64_t* aempty = bars + SC_MAX_STAGES;      // [SC_MAX_STAGES]
+  uint64_t* bfull  = bars + 2 * SC_MAX_STAGES;  // [1]
+  uint64_t* bempty = bfull + 1;                 // [1]
+  uint64_t* tfull  = bempty + 1;                // [2]
+  uint64_t* tempty = tfull + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SC_MAX_STAGES; ++i) { ptx::mbar_init(&afull[i], 1); ptx::mbar_init(&aempty[i], 1); }
+    ptx::mbar_init(bfull, 1);
+    ptx::mbar_init(bempty, 2);  // one arrival per MMA issuer
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], SC_EPI_WARPS / SC_SETS); }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb              = p.nkb;
+  const uint32_t stage_bytes = static_cast<uint32_t>(nkb) * SC_A_KB_BYTES;
+  const uint32_t n_stages    = static_cast<uint32_t>(p.n_stages);
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    const uint64_t pol = ptx::policy_evict_last();
+    uint32_t t_it = 0, it_local = 0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int ch    = static_cast<int>(item / p.tiles_sel);
+      const int mt0   = ch * p.chunk;
+      const int mt1   = min(mt0 + p.chunk, p.tiles_m);
+      ptx::mbar_wait(bempty, (it_local & 1) ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(bfull, static_cast<uint32_t>(nkb) * SC_B_KB_BYTES);
+        for (int kb = 0; kb < nkb; ++kb)
+          ptx::tma_load_2d(b_base + kb * SC_B_KB_BYTES, &tmap_b, bfull, kb * 64, n_blk * TC_BN, pol);
+      }
+      __syncwarp();
+      for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
+        const uint32_t s = t_it % n_stages, ph = (t_it / n_stages) & 1;
+        ptx::mbar_wait(&aempty[s], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&afull[s], stage_bytes);
+          for (int kb = 0; kb < nkb; ++kb)
+            ptx::tma_load_2d(a_base + s * stage_bytes + kb * SC_A_KB_BYTES, &tmap_a, &afull[s], kb * 64, mt * TC_BM,
+                             pol);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 || warp == SC_MMA2_WARP) {
+    // ================================ MMA issuers ==================================
+    // Two issuer warps, one per accumulator stage (even / odd tiles).  tcgen05.mma issue blocks while
+    // the tensor pipe's queue is full, i.e. for most of a tile's execution; with a single issuer the
+    // pipe then idles during that warp's bookkeeping for the next tile (barrier polls, descriptors,
+    // commits: ~500 cycles against ~770 of tensor work).  The two warps' tiles are independent (other
+    // accumulator, other x stage), so the order in which the pipe receives them does not matter.
+    const uint32_t parity = warp == 1 ? 0u : 1u;
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(TC_BM, TC_BN);
+    const uint32_t d = tmem_base + parity * TC_BN;
+    uint32_t t_it = 0, it_local = 0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+      const int ch  = static_cast<int>(item / p.tiles_sel);
+      const int mt0 = ch * p.chunk;
+      const int mt1 = min(mt0 + p.chunk, p.tiles_m);
+      int mt        = mt0 + static_cast<int>((parity ^ t_it) & 1u);
+      if (mt >= mt1) {  // no tile of this item is ours: still release our half of the y-block barrier
+        if (ptx::elect_one()) ptx::mbar_arrive(bempty);
+        __syncwarp();
+      } else {
+        ptx::mbar_wait(bfull, it_local & 1);
+      }
+      for (; mt < mt1; mt += 2) {
+        const uint32_t tt = t_it + static_cast<uint32_t>(mt - mt0);
+        const uint32_t s = tt % n_stages, ph = (tt / n_stages) & 1;
+        ptx::mbar_wait(&tempty[parity], ((tt >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&afull[s], ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t da = ptx::umma_desc_sw64(ptx::smem_u32(a_base + s * stage_bytes));
+          const uint64_t db = ptx::umma_desc_sw64(ptx::smem_u32(b_base));
+#pragma unroll
+          for (int kb = 0; kb < SC_MAX_KB; ++kb) {
+            if (kb < nkb) {
+              // descriptor address units are 16 B: k[0,16) of the 64-byte row at +0, k[16,32) at +2
+              const uint64_t dak = da + static_cast<uint64_t>(kb * (SC_A_KB_BYTES >> 4));
+              const uint64_t dbk = db + static_cast<uint64_t>(kb * (SC_B_KB_BYTES >> 4));
+              ptx::mma_f16_ss(d, dak, dbk, idesc, kb > 0 ? 1u : 0u);
+              ptx::mma_f16_ss(d, dak + 2, dbk + 2, idesc, 1u);
+            }
+          }
+          ptx::mma_commit(&aempty[s]);
+          if (mt + 2 >= mt1) ptx::mma_commit(bempty);  // our last tile of the item
+          ptx::mma_commit(&tfull[parity]);
+        }
+        __syncwarp();
+      }
+      t_it += static_cast<uint32_t>(mt1 - mt0);
+    }
+  } else {
+    // ================================ epilogue warps ===============================
+    const int w   = warp - 2;        // 0..15
+    const int set = SC_SETS == 2 ? (w >> 3) : 0;  // SC_SETS == 2: accumulator stage (tile parity) this warp drains
+    const int q   = warp & 3;        // TMEM lane quarter this warp may read: tile rows [32q, 32q+32)
+    const int g   = SC_SETS == 2 ? ((w & 7) >> 2) : (w >> 2);  // column slice of the tile: [SC_CW g, SC_CW (g+1))
+    const int et  = threadIdx.x - 64;
+    const float cf     = __ldg(p.coef);
+    const uint64_t cf2 = pk(cf, cf);
+    const float2 aux_none = make_float2(__int_as_float(0xff800000), 0.f);  // rows beyond m: threshold NaN, never taken
+    uint32_t t_it = 0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int ch    = static_cast<int>(item / p.tiles_sel);
+      const int mt0   = ch * p.chunk;
+      const int mt1   = min(mt0 + p.chunk, p.tiles_m);
+      // this warp's first tile of the item, and its row data (global-load latency hides behind the
+      // column-term barrier below)
+      int mt_own = SC_SETS == 2 ? mt0 + ((set ^ static_cast<int>(t_it)) & 1) : mt0;
+      float2 aux_nxt = aux_none;
+      {
+        const int64_t r = static_cast<int64_t>(mt_own) * TC_BM + q * 32 + lane;
+        if (mt_own < mt1 && r < p.m) aux_nxt = __ldg(&p.aux[r]);
+      }
+      // per-column terms of this y block (shared by every tile of the item)
+      ptx::bar_sync(1, 32 * SC_EPI_WARPS);
+      if (et < TC_BN) {
+        const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
+        float tv = __int_as_float(0x7f800000), nyv = 0.f;  // +inf: never a candidate
+        if (gj < p.n) {
+          tv  = __ldg(&p.yt[gj]);
+          nyv = sqrtf(tv) * (1.05f / 512.f);
+          tv  = tv - tv * (1.f / 2097152.f);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nyv = fmaxf(nyv, __shfl_xor_sync(0xffffffffu, nyv, o));
+        if (lane == 0) col_ny[et >> 5] = nyv;
+        col_tb[et] = tv;
+      }
+      ptx::bar_sync(1, 32 * SC_EPI_WARPS);
+      float ny_max = 0.f;
+#pragma unroll
+      for (int i = 0; i < TC_BN / 32; ++i) ny_max = fmaxf(ny_max, col_ny[i]);
+      const float yn_max = (ny_max * (512.f / 1.05f)) * (ny_max * (512.f / 1.05f));  // max |y_j|^2 of the block
+
+      const uint32_t t_item0 = t_it;
+      for (; mt_own < mt1; mt_own += SC_SETS) {
+        const uint32_t tt   = t_item0 + static_cast<uint32_t>(mt_own - mt0);  // global tile counter of this tile
+        const int64_t row   = static_cast<int64_t>(mt_own) * TC_BM + q * 32 + lane;
+        const float2 aux_c  = aux_nxt;
+        aux_nxt             = aux_none;
+        if (mt_own + SC_SETS < mt1 && row + SC_SETS * TC_BM < p.m) aux_nxt = __ldg(&p.aux[row + SC_SETS * TC_BM]);
+        // U_i - |x_i|^2 + |x_i| * max margin, nudged up so that it stays an upper bound
+        float thr = fmaf(-aux_c.y, ny_max, aux_c.x);
+        thr       = thr + fabsf(thr) * (1.f / 4194304.f);
+
+        const uint32_t as = tt & 1, aph = (tt >> 1) & 1;
+        ptx::mbar_wait(&tfull[as], aph);
+        ptx::tc_fence_after();
+        const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * TC_BN + g * SC_CW;
+        const int cb          = g * SC_CW;
+        uint32_t ra[16], rb[16];
+        unsigned hitmask = 0;  // bit gp: some column of the gp-th 32-column group reaches the threshold
+        float m0, m1, m2, m3;
+#define B2D_GROUP_BEGIN m0 = m1 = m2 = m3 = __int_as_float(0x7f800000);
+#define B2D_GROUP_END(GP) hitmask |= (fminf(min3(m0, m1, m2), m3) <= thr) ? (1u << (GP)) : 0u;
+        ptx::tmem_ld_32x16(t_base, ra);
+#pragma unroll
+        for (int gp = 0; gp < SC_CW / 32; ++gp) {  // two register buffers: the next load is in flight during the math
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x16(t_base + 32 * gp + 16, rb);
+          B2D_GROUP_BEGIN
+          B2D_SCREEN_FRAGMENT(ra, cb + 32 * gp)
+          ptx::tmem_ld_wait();
+          if (gp + 1 < SC_CW / 32) ptx::tmem_ld_32x16(t_base + 32 * gp + 32, ra);
+          B2D_SCREEN_FRAGMENT(rb, cb + 32 * gp + 16)
+          B2D_GROUP_END(gp)
+        }
+#undef B2D_GROUP_BEGIN
+#undef B2D_GROUP_END
+        unsigned long long cmask = 0ull;  // columns of this row (bit = column - cb) that go to the exact pass
+        float vmin = __int_as_float(0x7f800000);
+        if (__any_sync(0xffffffffu, hitmask != 0u)) {
+          // rare (a per cent or two of the warp-tiles): some column of some row of this warp can still
+          // hold the minimum.  The accumulator is still ours: read the 32-column groups concerned again
+          // and note every column whose lower bound reaches the threshold.
+#pragma unroll 1
+          for (int gp = 0; gp < SC_CW / 32; ++gp) {
+            const bool mine = (hitmask >> gp) & 1u;
+            if (!__any_sync(0xffffffffu, mine)) continue;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = 32 * gp + 16 * h;
+              ptx::tmem_ld_32x16(t_base + c0, ra);
+              ptx::tmem_ld_wait();
+              if (mine) {
+                unsigned bits = 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const float lv = fmaf(__uint_as_float(ra[c]), cf, col_tb[cb + c0 + c]);
+                  if (lv <= thr && lv < __int_as_float(0x7f800000)) {
+                    bits |= 1u << c;
+                    vmin = fminf(vmin, lv);
+                  }
+                }
+                cmask |= static_cast<unsigned long long>(bits) << c0;
+              }
+            }
+          }
+        }
+        // hand the accumulator back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+        if (cmask != 0ull) {
+          // every coarse value is also an UPPER bound of a real pair's distance (value + margin): later
+          // tiles of this row, here and on the other SMs, screen against the tighter bound
+          float nb = fmaf(-aux_c.y, ny_max, vmin);
+          nb += (fabsf(nb) + 2.f * (aux_c.y * aux_c.y + yn_max)) * (1.f / 2097152.f);
+          if (nb < aux_c.x) {
+            int* addr = reinterpret_cast<int*>(&p.aux[row].x);
+            int old   = __float_as_int(aux_c.x);
+            while (nb < __int_as_float(old)) {
+              const int seen = atomicCAS(addr, old, __float_as_int(nb));
+              if (seen == old) break;
+              old = seen;
+            }
+          }
+          while (cmask != 0ull) {
+            const int c = __ffsll(static_cast<long long>(cmask)) - 1;
+            cmask &= cmask - 1ull;
+            const unsigned slot = atomicAdd(p.cand_cnt, 1u);
+            if (slot < p.cand_cap)
+              p.cand[slot] = make_int2(static_cast<int>(row), n_blk * TC_BN + cb + c);
+            else
+              *p.overflow = 1u;
+          }
+        }
+      }
+      t_it += static_cast<uint32_t>(mt1 - mt0);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+#undef B2D_SCREEN_FRAGMENT
+
+}  // namespace b2d

@@ -155,3 +155,83 @@ def test_row_norm_against_reference_spec():
             _lib.check(L.b2d_row_norm(None, out.data_ptr(), xt.data_ptr(), cols, rows, cols, 2, 1))
             torch.cuda.synchronize()
             assert oracle.match_approx(out.cpu().numpy(), np.sqrt(oracle.row_norm_sq(x)), 1e-5)[0]
+
+
+# ---- screened search (64 < k <= 128, n >= 16384): exact sub-sampled pass + coarse screen + exact
+# re-evaluation of the candidates (raft_b200/csrc/screen_tc.cuh)
+
+@pytest.mark.parametrize("shape", [(2000, 40000, 96), (1500, 20000, 128), (513, 33001, 70), (129, 16384, 65)])
+@pytest.mark.parametrize("kind", ["blobs", "gauss"])
+def test_screened_nn_vs_oracle(shape, kind):
+    m, n, k = shape
+    if kind == "blobs":
+        x, y = blobs(m, n, k, seed=5)
+    else:
+        rng = np.random.default_rng(11)
+        x = (rng.standard_normal((m, k)) * 3).astype(np.float32)
+        y = (rng.standard_normal((n, k)) * 3 + 0.5).astype(np.float32)
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=False)
+    gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    tie_aware_index_check(gi, ri, x, y)
+    ok, msg = oracle.match_approx(gv, rv, 1e-4)
+    assert ok, msg
+
+
+def test_screened_nn_ties_duplicates_and_wild_norms():
+    """Duplicates of the nearest row in sampled and unsampled y blocks -> smallest index; rows whose
+    norms differ by orders of magnitude keep the screening bound valid."""
+    rng = np.random.default_rng(21)
+    n, k = 40000, 96
+    y = rng.standard_normal((n, k)).astype(np.float32) * 2
+    y[::7] *= 50.0          # large-norm rows in every block
+    y[3::11] *= 0.01        # tiny-norm rows
+    q = [100, 300, 8200, 8447, 25000, 39999]   # blocks 0 (sampled), 1, 32 (sampled), 32, 97, 156
+    x = y[q] + 1e-3
+    y[[20000, 39000]] = y[100]     # later duplicates of a row in a sampled block
+    y[[9000, 31000]] = y[300]      # later duplicates of a row in an unsampled block
+    gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
+    assert gi.cpu().tolist() == q
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=False)
+    assert (ri == np.array(q)).all()
+
+
+def test_screened_nn_overflow_falls_back_to_exact():
+    """All database rows identical: every column is a candidate, the list overflows and the exact
+    kernel re-runs on the device -- same answer as the small case (index 0, distance k)."""
+    y = np.ones((20000, 96), np.float32)
+    gi, gv = fused_l2_nn(torch.zeros(700, 96, device="cuda"), torch.from_numpy(y).cuda(), sqrt=False)
+    assert (gi == 0).all() and torch.allclose(gv, torch.full_like(gv, 96.0))
+    # near-duplicates: 20000 rows within 1e-4 of each other, the true minimum hidden at a late index
+    rng = np.random.default_rng(2)
+    y = (np.ones((20000, 96)) + rng.standard_normal((20000, 96)) * 1e-4).astype(np.float32)
+    x = rng.standard_normal((300, 96)).astype(np.float32)
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=False)
+    gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    # 20000 near-ties per row: the index is only defined up to fp32 resolution, the distance is not
+    d_got = ((x.astype(np.float64) - y[gi].astype(np.float64)) ** 2).sum(1)
+    assert np.all(np.abs(d_got - rv) <= 1e-5 * np.maximum(rv, 1.0))
+    assert oracle.match_approx(gv, rv, 1e-4)[0]
+
+
+def test_screened_sharded_matches_single():
+    """Shards large enough to be screened themselves; the second shard starts from the first one's keys."""
+    x, y = blobs(1000, 70000, 96, seed=9)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    i1, v1 = fused_l2_nn(xt, yt, sqrt=False)
+    L = _lib.lib()
+    h = DeviceResources()
+    m, k = x.shape
+    keys = torch.empty(m, dtype=torch.int64, device="cuda")
+    kvp = torch.empty((m, 2), dtype=torch.int32, device="cuda")
+    for r in range(2):
+        lo, hi = shard_bounds(y.shape[0], 2, r)
+        ys = yt[lo:hi].contiguous()
+        ws = h.workspace(L.b2d_fused_l2_nn_workspace_bytes(m, hi - lo, k))
+        _lib.check(L.b2d_fused_l2_nn_keys(h.stream_ptr, keys.data_ptr(), xt.data_ptr(), k, ys.data_ptr(), k, None,
+                                          None, m, hi - lo, k, lo, 1 if r == 0 else 0, ws.data_ptr(), ws.numel()))
+    _lib.check(L.b2d_fused_l2_nn_finalize(h.stream_ptr, kvp.data_ptr(), keys.data_ptr(), m, 0, ws.data_ptr(), ws.numel()))
+    h.sync()
+    assert (kvp[:, 0] == i1).all()
+    assert torch.equal(kvp[:, 1].view(torch.float32), v1)
