@@ -119,11 +119,12 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   w.has_lo = w.gmax + 3;
   w.xt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4));
   w.keys = reinterpret_cast<long long*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
-  // screened fusedL2NN scratch: thresholds, counters, candidate list (64 per row: ~50 expected on
-  // clustered data; overflow falls back to the exact pass on the device, never to a wrong answer)
-  w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(64 * m + (1 << 16), 0x7fffffff)) : 0u;
+  // screened fusedL2NN scratch: thresholds, counters, candidate list (128 per row and 1M-row chunk of y;
+  // ~54 measured on far-from-origin clusters; overflow falls back to the exact pass on the device,
+  // never to a wrong answer)
+  w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(128 * m + (1 << 16), 0x7fffffff)) : 0u;
   w.aux      = reinterpret_cast<float2*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
-  w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 16 : 0));
+  w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 32 : 0));
   w.cand     = reinterpret_cast<int2*>(c + take(static_cast<size_t>(w.cand_cap) * 8));
   w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
   w.xop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(m) * nkb * 128));
@@ -213,11 +214,7 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.nkb     = nkb_chunk ? nkb_chunk : nkb_total;
   p.tiles_m = static_cast<int>((p.m + TC_BM - 1) / TC_BM);
   p.tiles_n = static_cast<int>((p.n + TC_BN - 1) / TC_BN);
-  if (p.sel_mode == 0) p.tiles_sel = p.tiles_n;
-  else {
-    const int first = (p.tiles_n + p.sel_s - 1) / p.sel_s;  // blocks with index % sel_s == 0
-    p.tiles_sel     = p.sel_mode == 1 ? first : p.tiles_n - first;
-  }
+  p.tiles_sel = sel_count(p.tiles_n, p.sel_s, p.sel_lo, p.sel_hi);
   int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_sel;
   int64_t chunk = total / (static_cast<int64_t>(sms) * 6);
   if (chunk < 1) chunk = 1;
@@ -258,9 +255,10 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
                   : launch_tc_store<false, false>(s, ma, mb, md, p, grid, post);
 }
 
-// coarse screening pass of the screened fusedL2NN (screen_tc.cuh) over the y blocks with index % sel_s != 0
-static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_t n, int64_t k, int sel_s,
-                         unsigned* overflow)
+// coarse screening pass of the screened fusedL2NN (screen_tc.cuh) over the y blocks with
+// sel_lo <= index % sel_s < sel_hi
+static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_t n, int64_t k, int sel_s, int sel_lo,
+                         int sel_hi, unsigned* overflow, const unsigned* run_flag)
 {
   int sms = 0, cc = 0;
   int rc  = device_sms(&sms, &cc);
@@ -274,8 +272,8 @@ static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_
   p.n_stages = static_cast<int>(std::min<size_t>(SC_MAX_STAGES, SC_A_RING / (static_cast<size_t>(p.nkb) * SC_A_KB_BYTES)));
   p.tiles_m = static_cast<int>((m + TC_BM - 1) / TC_BM);
   const int tiles_n = static_cast<int>((n + TC_BN - 1) / TC_BN);
-  p.sel_mode = 2; p.sel_s = sel_s;
-  p.tiles_sel = tiles_n - (tiles_n + sel_s - 1) / sel_s;
+  p.sel_s = sel_s; p.sel_lo = sel_lo; p.sel_hi = sel_hi;
+  p.tiles_sel = sel_count(tiles_n, sel_s, sel_lo, sel_hi);
   // long runs of x tiles per y block: the y block load is not overlapped with the previous item
   int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_sel;
   int64_t chunk = total / (static_cast<int64_t>(sms) * 4);
@@ -285,7 +283,7 @@ static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_
   p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
   p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
   p.yt = w.yt; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
-  p.overflow = overflow;
+  p.overflow = overflow; p.run_flag = run_flag;
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb;
   rc = make_operand_map(&ma, w.xop, m, p.nkb, TC_BM, 0, 0, true);
@@ -487,6 +485,73 @@ size_t b2d_fused_l2_nn_workspace_bytes(int64_t m, int64_t n, int64_t k)
   return tc_layout(nullptr, m, n, k, true).bytes;
 }
 
+// one chunk of y (prep + search); keys carry the result so far (and act as the rows' bounds)
+static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                               const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int64_t idx_offset,
+                               void* workspace, int mode, int center, bool allow_screen)
+{
+  TcWorkspace w = tc_layout(workspace, m, n, k, true);
+  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, mode, center);
+  if (rc) return rc;
+  if (n == 0) return B2D_OK;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
+  const int nkb = static_cast<int>((k + 31) / 32);
+  // (k <= 64: the exact kernel is already epilogue-bound, screening would not pay)
+  const bool screen = mode == PREP_L2 && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && allow_screen;
+  if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+
+  // Screened search (screen_tc.cuh).  With S = 32 and r = index of a 256-row y block modulo S:
+  //   A  exact arg-min kernel on the blocks r == 0            -> every row has an upper bound
+  //   T  coarse 1-product screen on the blocks r == 1 (trial) -> candidates, tighter bounds
+  //      decide on the device: few candidates per row -> screening pays, go on with it; many (data
+  //      whose norms dwarf the nearest-neighbour distances, e.g. far-from-origin clusters: the
+  //      screen's margin is relative to |x||y|) -> the remaining blocks take the exact kernel
+  //   R  coarse screen on the blocks r >= 2                   (if screening pays)
+  //   E  exact re-evaluation of every candidate, straight from the fp32 inputs
+  //   X  exact kernel on r == 1 / r >= 2                      (only where candidates were dropped, or
+  //                                                            where screening was called off)
+  // Every launch after T is conditional on a device flag: no host round trip, no wrong answer.
+  constexpr int kSel = 32;
+  static const float tau = getenv("B2D_NN_TAU") ? static_cast<float>(atof(getenv("B2D_NN_TAU"))) : 6.0f;
+  unsigned* flags = w.cand_cnt;  // [0] count [1] overflow [2] go_screen [3] go_exact [4] redo_trial [5] count after T
+  p.sel_s = kSel; p.sel_lo = 0; p.sel_hi = 1;
+  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+  if (rc) return rc;
+  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
+                                                                         w.cand, flags, m, n, idx_offset);
+  B2D_CUDA(cudaGetLastError());
+  rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr);
+  if (rc) return rc;
+  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 1);
+  B2D_CUDA(cudaGetLastError());
+  rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2);
+  if (rc) return rc;
+  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 2);
+  B2D_CUDA(cudaGetLastError());
+  int sms = 0, cc = 0;
+  rc = device_sms(&sms, &cc);
+  if (rc) return rc;
+  nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
+                                          ldy, static_cast<int>(k), idx_offset);
+  B2D_CUDA(cudaGetLastError());
+  p.sel_lo = 1; p.sel_hi = 2; p.run_flag = flags + 4;
+  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+  if (rc) return rc;
+  p.sel_lo = 2; p.sel_hi = kSel; p.run_flag = flags + 3;
+  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+  if (rc) return rc;
+  if (getenv("B2D_NN_DEBUG")) {  // diagnostics only: synchronises
+    unsigned h[6];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, flags, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "b2d nn: candidates %u (%.2f/row; after trial %.3f/row) overflow %u go_screen %u go_exact %u redo_trial %u\n",
+            h[0], double(h[0]) / m - 1.0, double(h[5]) / m - 1.0, h[1], h[2], h[3], h[4]);
+  }
+  return B2D_OK;
+}
+
 static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
                          const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int64_t idx_offset,
                          int init_keys, void* workspace, size_t workspace_bytes, int mode, int center)
@@ -502,44 +567,25 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   if (!workspace || workspace_bytes < need)
     return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
   if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
-  TcWorkspace w = tc_layout(workspace, m, n, k, true);
+  static const bool screen_off = getenv("B2D_NN_SCREEN") != nullptr && atoi(getenv("B2D_NN_SCREEN")) == 0;
   if (init_keys) {
     minloc_init_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), m);
     B2D_CUDA(cudaGetLastError());
   }
-  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, mode, center);
-  if (rc) return rc;
-  if (n == 0) return B2D_OK;
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
-  const int nkb = static_cast<int>((k + 31) / 32);
-  static const bool screen_off = getenv("B2D_NN_SCREEN") != nullptr && atoi(getenv("B2D_NN_SCREEN")) == 0;
-  // (k <= 64: the exact kernel is already epilogue-bound, screening would not pay)
-  const bool screen = mode == PREP_L2 && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && !screen_off;
-  if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
-
-  // Screened search (see expanded_tc.cuh): exact on every 8th y block -> bound; coarse 1-product pass
-  // over the rest -> candidates; exact re-evaluation of the candidates; exact fallback only if the
-  // candidate list overflowed (decided on the device: no host round trip).
-  constexpr int kSel = 32;
-  p.sel_mode = 1; p.sel_s = kSel;
-  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
-  if (rc) return rc;
-  unsigned* overflow = w.cand_cnt + 1;
-  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
-                                                                         w.cand, w.cand_cnt, overflow, m, n, idx_offset);
-  B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, overflow);
-  if (rc) return rc;
-  int sms = 0, cc = 0;
-  rc = device_sms(&sms, &cc);
-  if (rc) return rc;
-  nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
-                                          ldy, static_cast<int>(k), idx_offset);
-  B2D_CUDA(cudaGetLastError());
-  p.sel_mode = 2; p.run_flag = overflow;  // the other blocks, exactly: runs only if candidates were dropped
-  return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+  // The screened search (below) works through y in chunks of 2^20 rows: the candidate list is sized per
+  // chunk, and every chunk starts from the bounds the earlier ones left in the keys.
+  const int nkb_all    = static_cast<int>((k + 31) / 32);
+  const bool screen_ok = mode == PREP_L2 && nkb_all >= 3 && nkb_all <= TC_MAX_RES_KB && !screen_off;
+  constexpr int64_t kChunkRows = 1 << 20;
+  if (!screen_ok || n <= kChunkRows)
+    return fused_nn_keys_chunk(s, keys, x, ldx, y, ldy, xn, yn, m, n, k, idx_offset, workspace, mode, center, screen_ok);
+  for (int64_t off = 0; off < n; off += kChunkRows) {
+    const int64_t nc = std::min<int64_t>(kChunkRows, n - off);
+    int rc = fused_nn_keys_chunk(s, keys, x, ldx, y + off * ldy, ldy, xn, yn ? yn + off : nullptr, m, nc, k,
+                                 idx_offset + off, workspace, mode, center, true);
+    if (rc) return rc;
+  }
+  return B2D_OK;
 }
 
 int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,

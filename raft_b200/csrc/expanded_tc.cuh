@@ -71,8 +71,8 @@ struct TcParams {
   int64_t m, n;
   int nkb;                // k-blocks of 32 source columns
   int tiles_m, tiles_n;   // ceil(m/128), ceil(n/256)
-  int tiles_sel;          // y blocks this launch visits (all of them unless sel_mode != 0)
-  int sel_mode, sel_s;    // 0: every y block; 1: blocks with index % sel_s == 0; 2: the others
+  int tiles_sel;          // y blocks this launch visits (all of them unless sel_s > 1)
+  int sel_s, sel_lo, sel_hi;  // sel_s > 1: only the y blocks with sel_lo <= index % sel_s < sel_hi
   int chunk;              // m-tiles per work item
   int chunks_m;           // ceil(tiles_m/chunk)
   int64_t n_items;        // tiles_n * chunks_m
@@ -97,12 +97,19 @@ static_assert((size_t)TC_STAGES_STR * (TC_A_BYTES + TC_B_BYTES) <= TC_SMEM_OPERA
 constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_BN * 4 + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
 
-// index of the s-th selected y block (see TcParams::sel_mode)
-__device__ __forceinline__ int sel_to_blk(int s, int mode, int S)
+// index of the s-th selected y block (see TcParams::sel_s)
+__host__ __device__ __forceinline__ int sel_to_blk(int s, int S, int lo, int hi)
 {
-  if (mode == 0) return s;
-  if (mode == 1) return s * S;
-  return s + s / (S - 1) + 1;
+  if (S <= 1) return s;
+  const int w = hi - lo;
+  return (s / w) * S + lo + (s % w);
+}
+// how many of the blocks [0, tiles_n) are selected
+__host__ __device__ __forceinline__ int sel_count(int tiles_n, int S, int lo, int hi)
+{
+  if (S <= 1) return tiles_n;
+  const int rem = tiles_n % S;
+  return (tiles_n / S) * (hi - lo) + max(0, min(rem, hi) - lo);
 }
 
 // float -> int whose signed order equals the float order
@@ -210,7 +217,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint64_t pol = ptx::policy_evict_last();
     uint32_t a_it = 0, it_local = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_s, p.sel_lo, p.sel_hi);
       const int ch    = static_cast<int>(item / p.tiles_sel);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
@@ -335,7 +342,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint64_t pol_st = ptx::policy_evict_first();
     const uint64_t cf2 = pk(cf, cf);
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_s, p.sel_lo, p.sel_hi);
       const int ch    = static_cast<int>(item / p.tiles_sel);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
@@ -699,11 +706,14 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, int64_
 // so every finalist is measured with the same arithmetic.
 
 // after the exact sub-sampled pass: thr = incumbent distance, incumbent -> candidate, keys reset
-__global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, int2* cand, unsigned* cnt,
-                               unsigned* overflow, int64_t m, int64_t n, int64_t idx_offset)
+__global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, int2* cand, unsigned* flags,
+                               int64_t m, int64_t n, int64_t idx_offset)
 {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i == 0) { *cnt = static_cast<unsigned>(m); *overflow = 0u; }
+  if (i == 0) {  // [0] candidate count [1] overflow [2] go_screen [3] go_exact [4] redo_trial [5] count after the trial
+    flags[0] = static_cast<unsigned>(m);
+    flags[1] = flags[2] = flags[3] = flags[4] = flags[5] = 0u;
+  }
   if (i >= m) return;
   const long long key = keys[i];
   float t             = __int_as_float(0x7f800000);
@@ -721,6 +731,23 @@ __global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, in
   const float xn = xt[i];
   aux[i]  = make_float2((t - xn) + (t + xn) * (1.f / 2097152.f), -sqrtf(xn));
   cand[i] = c;
+}
+
+// device-side control of the screened search (fused_nn_keys in api.cu)
+//   stage 1, after the trial screen: candidates per row above tau (or a full list) -> exact for the rest
+//   stage 2, after the main screen : a full list -> exact for the blocks it covered
+__global__ void nn_decide_kernel(unsigned* flags, unsigned m, float tau, int stage)
+{
+  if (stage == 1) {
+    flags[5]            = flags[0];
+    const unsigned redo = flags[1] != 0u;
+    const bool many     = static_cast<float>(flags[0] - m) > tau * static_cast<float>(m);
+    flags[4]            = redo;
+    flags[3]            = (redo || many) ? 1u : 0u;
+    flags[2]            = flags[3] ? 0u : 1u;
+  } else if (flags[2] != 0u && flags[1] != 0u) {
+    flags[3] = 1u;
+  }
 }
 
 // one warp per candidate: d = sum (x_i - y_j)^2 in fp32 from the original inputs

@@ -22,8 +22,9 @@
 // (1M x 1M x 96, cycles per tile): the first version re-used the exact kernel's roles and took 2300
 // -- the single MMA warp spent 740 issuing (tcgen05.mma issue blocks while the pipe's queue is full),
 // 810 + 690 in barrier polls and bookkeeping while the pipe idled, and the epilogue exposed one TMEM
-// load latency per fragment.  This kernel: 1150.  Isolation runs: operands + MMAs alone 1010,
-// epilogue alone 1100, synchronisation skeleton alone 620.
+// load latency per fragment.  This kernel: ~1600 with everything on; isolation runs: operands + MMAs
+// alone 1010, epilogue alone 1100, synchronisation skeleton alone 620 -- the two halves still
+// contend (TMEM ports, issue slots) instead of overlapping fully.
 //   operands   hi halves only: TMA boxes of 32 fp16 (64 B, SWIZZLE_64B) out of the packed
 //              [hi32|lo32] k-blocks; a stage is one whole x tile (nkb x 8 KB), 5-6 stages deep,
 //              one mbarrier round trip per TILE; the y block (nkb x 16 KB) is resident per item
@@ -65,7 +66,7 @@ struct ScreenParams {
   int nkb;                // k-blocks of 32 source columns (<= SC_MAX_KB)
   int n_stages;           // x-tile stages in the ring (host: min(SC_MAX_STAGES, SC_A_RING / (nkb * 8 KB)))
   int tiles_m, tiles_sel; // ceil(m/128); y blocks this launch visits
-  int sel_mode, sel_s;    // as TcParams
+  int sel_s, sel_lo, sel_hi;  // as TcParams
   int chunk, chunks_m;    // m-tiles per work item
   int64_t n_items;
   const float* yt;        // [n] |y_j|^2
@@ -75,6 +76,7 @@ struct ScreenParams {
   unsigned* cand_cnt;     // ... its fill counter ...
   unsigned cand_cap;      // ... capacity ...
   unsigned* overflow;     // ... and overflow flag (then the exact pass re-runs)
+  const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
 };
 
 // 16 columns of this thread's row: lower bounds folded into four running minima (no branches: the
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const ScreenParams p)
 {
+  if (p.run_flag != nullptr && __ldg(p.run_flag) == 0u) return;  // conditional launch (no host round trip)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* b_base  = smem;
@@ -141,7 +144,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint64_t pol = ptx::policy_evict_last();
     uint32_t t_it = 0, it_local = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_s, p.sel_lo, p.sel_hi);
       const int ch    = static_cast<int>(item / p.tiles_sel);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);
@@ -225,7 +228,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const float2 aux_none = make_float2(__int_as_float(0xff800000), 0.f);  // rows beyond m: threshold NaN, never taken
     uint32_t t_it = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_mode, p.sel_s);
+      const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_s, p.sel_lo, p.sel_hi);
       const int ch    = static_cast<int>(item / p.tiles_sel);
       const int mt0   = ch * p.chunk;
       const int mt1   = min(mt0 + p.chunk, p.tiles_m);

@@ -13,6 +13,7 @@ from ..common import auto_convert_output, auto_sync_handle, cai_wrapper, device_
 from .distance_type import resolve_metric
 
 KVP_DTYPE = np.dtype([("key", np.int32), ("value", np.float32)])  # raft::KeyValuePair<int,float>
+SHARD_HEAD_ROWS = 1 << 15  # rows of every shard searched before the first exchange of bounds (fused_l2_nn_sharded)
 
 
 def _check_xy(X, Y):
@@ -86,13 +87,13 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, hi
 
 
-def fused_l2_nn_sharded(X, Y_shard, idx_offset, sqrt=True, handle=None, group=None, keys=None):
+def fused_l2_nn_sharded(X, Y_shard, idx_offset, sqrt=True, handle=None, group=None, keys=None, head_rows=None):
     """Multi-GPU fusedL2NN: every rank holds all queries X [m,k] and its own row-block Y_shard of
     the database (global row index of its first row = idx_offset).  One process per GPU;
     `group` is a torch.distributed process group (NCCL over NVLink on the GPU box).
 
     Returns (indices int32 [m] -- GLOBAL database rows, distances float32 [m]) on every rank.
-    The only collective is all_reduce(MIN) over m packed int64 keys: NCCL has no MINLOC, and
+    The only collective is all_reduce(MIN) over m packed int64 keys (twice for large shards, see below): NCCL has no MINLOC, and
     signed 64-bit MIN over (ordered distance bits << 32 | index) is exactly raft::argmin_op
     (smaller value first, then smaller index; cpp/include/raft/core/operators.hpp:187-194)."""
     import torch.distributed as dist
@@ -110,9 +111,24 @@ def fused_l2_nn_sharded(X, Y_shard, idx_offset, sqrt=True, handle=None, group=No
         if keys is None:
             keys = torch.empty(m, dtype=torch.int64, device=handle.device)
         kvp = torch.empty((m, 2), dtype=torch.int32, device=handle.device)
-        _lib.check(L.b2d_fused_l2_nn_keys(handle.stream_ptr, keys.data_ptr(), x_cai.data, k, y_cai.data, k,
-                                          None, None, m, n, k, int(idx_offset), 1, ws.data_ptr(), ws.numel()))
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        # Two exchanges when the shard is large: the first, after a small head of every shard, gives
+        # each rank the best distance found ANYWHERE so far -- the screened search (screen_tc.cuh) then
+        # starts the rest of its shard from global bounds and keeps far fewer candidates.  No row is
+        # visited twice: the second call continues behind the head with the reduced keys.
+        if head_rows is None:
+            head = SHARD_HEAD_ROWS if (multi and n >= 4 * SHARD_HEAD_ROWS) else 0
+        else:
+            head = max(0, min(int(head_rows), n))
+        if head:
+            _lib.check(L.b2d_fused_l2_nn_keys(handle.stream_ptr, keys.data_ptr(), x_cai.data, k, y_cai.data, k,
+                                              None, None, m, head, k, int(idx_offset), 1, ws.data_ptr(), ws.numel()))
+            if multi:
+                dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+        _lib.check(L.b2d_fused_l2_nn_keys(handle.stream_ptr, keys.data_ptr(), x_cai.data, k,
+                                          y_cai.data + head * k * 4, k, None, None, m, n - head, k,
+                                          int(idx_offset) + head, 0 if head else 1, ws.data_ptr(), ws.numel()))
+        if multi:
             dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
         _lib.check(L.b2d_fused_l2_nn_finalize(handle.stream_ptr, kvp.data_ptr(), keys.data_ptr(), m,
                                               1 if sqrt else 0, ws.data_ptr(), ws.numel()))

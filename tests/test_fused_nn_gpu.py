@@ -235,3 +235,19 @@ def test_screened_sharded_matches_single():
     h.sync()
     assert (kvp[:, 0] == i1).all()
     assert torch.equal(kvp[:, 1].view(torch.float32), v1)
+
+
+def test_sharded_head_exchange_path_matches_single():
+    """fused_l2_nn_sharded's two-stage form (head of the shard, exchange of bounds, rest of the shard)
+    visits every row once and returns what the one-call form returns."""
+    rng = np.random.default_rng(13)
+    x = (rng.standard_normal((1200, 96)) * 3).astype(np.float32)
+    y = (rng.standard_normal((80000, 96)) * 3).astype(np.float32)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    i1, v1 = fused_l2_nn(xt, yt, sqrt=True)
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=True)
+    tie_aware_index_check(i1.cpu().numpy(), ri, x, y)
+    for head in (0, 32768, 50000, 80000):
+        i2, v2 = fused_l2_nn_sharded(xt, yt, 0, sqrt=True, head_rows=head)
+        # every finalist of the screened search is measured with the same direct fp32 arithmetic
+        assert (i2 == i1).all() and torch.equal(v2, v1)
