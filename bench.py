@@ -340,6 +340,7 @@ def run_fused_nn_multi(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_src = measured_peaks()
     m, n, k = FUSED_NN["m"], FUSED_NN["n"], FUSED_NN["k"]

@@ -114,8 +114,13 @@ int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float
 
 /* Multi-GPU building blocks.  keys[i] = (order-preserving bits of ||x_i - y_j||^2 << 32)
  * | (j + idx_offset), reduced with signed 64-bit MIN: over this GPU's y shard here, then across
- * GPUs by the caller's all-reduce(INT64, MIN).  init_keys != 0 resets keys to +max first.
- * b2d_fused_l2_nn_finalize unpacks (clamp at 0, optional sqrt). */
+ * GPUs by the caller's all-reduce(INT64, MIN).  init_keys != 0 resets keys to +max first;
+ * init_keys == 0 continues from the keys an earlier call or another GPU left (they also serve as
+ * starting bounds of the screened search, so exchanging keys early makes the rest of a shard
+ * cheaper -- INTEGRATION.md section 3).  b2d_fused_l2_nn_finalize unpacks (clamp at 0, optional sqrt).
+ * For 64 < k <= 128 and n >= 16384 the result is produced by a screened search (exact tensor pass
+ * on 1/32 of y, 1-product lower-bound screen on the rest, exact fp32 re-evaluation of the
+ * candidates, device-side fallback to the exact pass): same answer, about a third of the work. */
 int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y,
                          int64_t ldy, const float* xn, const float* yn, int64_t m, int64_t n,
                          int64_t k, int64_t idx_offset, int init_keys, void* workspace,
