@@ -128,6 +128,17 @@ int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
 int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys, int64_t m,
                              int do_sqrt, const void* workspace, size_t workspace_bytes);
 
+/* Fused brute-force kNN for the L2 metrics (replaces raft::neighbors::brute_force::knn /
+ * fused_l2_knn, removed with the distance package -- CHANGELOG.md:59-60 -- and the pair
+ * pairwise_distance + raft::matrix::select_k, cpp/include/raft/matrix/select_k.cuh:73-106):
+ * out_idx[i, 0..n_neighbors) = rows of y nearest to x_i in ascending (distance, index) order,
+ * out_dist the squared (do_sqrt != 0: Euclidean) distances.  The m x n matrix is never written.
+ * n_neighbors <= 64, k <= 320.  The call synchronises the stream once per database pass. */
+size_t b2d_knn_l2_workspace_bytes(int64_t m, int64_t n, int64_t k, int64_t n_neighbors);
+int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, int64_t ldx, const float* y,
+               int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, int do_sqrt,
+               void* workspace, size_t workspace_bytes);
+
 /* out[r] = norm of row r of x:[rows,k] (L2Norm = sum of squares; do_sqrt applies sqrt_op as
  * fin_op, cpp/include/raft/linalg/norm.cuh:118-147). */
 int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k,

@@ -12,7 +12,7 @@ import numpy as np
 __all__ = [
     "DistanceType", "pairwise_distance", "fused_l2_nn", "row_norm_sq", "argmin_op",
     "row_argmin", "compare_approx", "match_approx", "make_blobs", "EXPANDED", "UNEXPANDED",
-    "pack_minloc", "unpack_minloc",
+    "pack_minloc", "unpack_minloc", "knn_l2",
 ]
 
 
@@ -181,6 +181,32 @@ def fused_l2_nn(x, y, sqrt: bool = False, block: int = 4096):
     if sqrt:
         best_v = np.sqrt(best_v)
     return best_i.astype(np.int32), best_v
+
+
+def knn_l2(x, y, n_neighbors: int, sqrt: bool = False, block: int = 4096):
+    """out[i, :] = the n_neighbors rows of y nearest to x_i, ascending by (squared L2 distance, index).
+
+    Restates what the reference's callers composed from raft::distance::pairwise_distance (L2Expanded)
+    followed by raft::matrix::select_k(select_min = true, sorted = true)
+    (cpp/include/raft/matrix/select_k.cuh:73-106; removed fused form: brute_force::fused_l2_knn,
+    CHANGELOG.md:59-60) -- SURVEY.md 8(f2).  Returns (idx int64[m, kk], val fp64[m, kk])."""
+    x64 = np.ascontiguousarray(x, dtype=np.float64)
+    y64 = np.ascontiguousarray(y, dtype=np.float64)
+    m, n = x64.shape[0], y64.shape[0]
+    kk = int(n_neighbors)
+    best_v = np.full((m, kk), np.inf)
+    best_i = np.full((m, kk), np.iinfo(np.int64).max, dtype=np.int64)
+    for j0 in range(0, n, block):
+        d = _block(x64, y64[j0:j0 + block], DistanceType.L2Expanded, 2.0)
+        idx = np.broadcast_to(np.arange(j0, j0 + d.shape[1], dtype=np.int64), d.shape)
+        v = np.concatenate([best_v, d], axis=1)
+        i = np.concatenate([best_i, idx], axis=1)
+        order = np.lexsort((i, v), axis=1)[:, :kk]       # primary key: distance, then index
+        best_v = np.take_along_axis(v, order, axis=1)
+        best_i = np.take_along_axis(i, order, axis=1)
+    if sqrt:
+        best_v = np.sqrt(best_v)
+    return best_i, best_v
 
 
 def compare_approx(a, b, eps):

@@ -240,6 +240,10 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
     return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
                     : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
   }
+  if (epi == EPI_TOPK) {
+    return resident ? launch_tc_inst<true, EPI_TOPK, POST_NONE, false>(s, ma, mb, md, p, grid)
+                    : launch_tc_inst<false, EPI_TOPK, POST_NONE, false>(s, ma, mb, md, p, grid);
+  }
   // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
   // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
   // unaligned outputs take the direct register->global path
@@ -655,6 +659,116 @@ int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float
   if (rc) return rc;
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
     reinterpret_cast<KvpIF*>(out), w.keys, m, 0, init_out ? 0 : 1);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused brute-force kNN: raft::neighbors::brute_force::knn / fused_l2_knn for the
+// L2 metrics without ever writing the m x n matrix (expanded_tc.cuh, EPI_TOPK).
+
+static size_t knn_topk_offset(int64_t m, int64_t n, int64_t k) { return align_up(tc_layout(nullptr, m, n, k, true).bytes, 1024); }
+
+size_t b2d_knn_l2_workspace_bytes(int64_t m, int64_t n, int64_t k, int64_t n_neighbors)
+{
+  if (m < 0 || n < 0 || k < 0 || n_neighbors < 1 || n_neighbors > KNN_MAX_K) return static_cast<size_t>(-1);
+  return knn_topk_offset(m, n, k) + align_up(static_cast<size_t>(m) * n_neighbors * 8, 1024);
+}
+
+namespace {
+struct KnnCtx {
+  cudaStream_t s;
+  TcWorkspace w;
+  TcParams p;       // m, knn_* set; n / idx_offset per pass
+  int64_t k;
+  int nkb;
+  long long* topk;
+  float* thr;
+  unsigned* cnt;
+  unsigned* overflow;
+  int kk;
+};
+}  // namespace
+
+// one pass over y rows [off, off + width): append, then fold into the top-k; a pass whose lists
+// overflowed (more than KNN_CAP entries for some row: ordered / adversarial data) is dropped and
+// repeated as two halves -- a width of KNN_CAP cannot overflow
+static int knn_pass(KnnCtx& c, int64_t off, int64_t width)
+{
+  TcWorkspace w2 = c.w;
+  w2.yop         = c.w.yop + static_cast<size_t>(off) * c.nkb * 64;
+  w2.yt          = c.w.yt + off;
+  TcParams p     = c.p;
+  p.n            = width;
+  p.idx_offset   = off;
+  int rc         = launch_tc(c.s, w2, p, c.k, EPI_TOPK, POST_NONE);
+  if (rc) return rc;
+  unsigned of = 0;
+  B2D_CUDA(cudaMemcpyAsync(&of, c.overflow, sizeof(of), cudaMemcpyDeviceToHost, c.s));
+  B2D_CUDA(cudaStreamSynchronize(c.s));
+  const unsigned blocks = static_cast<unsigned>((c.p.m + 255) / 256);
+  if (of != 0u) {
+    if (width <= KNN_CAP) return fail(B2D_ERR_CUDA, "internal: kNN list overflow at minimum pass width");
+    knn_reset_kernel<<<blocks, 256, 0, c.s>>>(c.cnt, c.overflow, c.p.m);
+    B2D_CUDA(cudaGetLastError());
+    const int64_t half = std::max<int64_t>(KNN_CAP, (width / 2 + KNN_CAP - 1) / KNN_CAP * KNN_CAP);
+    rc = knn_pass(c, off, std::min(half, width));
+    if (rc) return rc;
+    if (half < width) rc = knn_pass(c, off + half, width - half);
+    return rc;
+  }
+  knn_merge_kernel<<<static_cast<unsigned>((c.p.m + 7) / 8), 256, 0, c.s>>>(c.topk, c.p.knn_cand, c.cnt, c.thr, c.p.m, c.kk);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, int64_t ldx, const float* y,
+               int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, int do_sqrt, void* workspace,
+               size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
+  if (n_neighbors < 1 || n_neighbors > n) return fail(B2D_ERR_INVALID_ARG, "n_neighbors must be in [1, n]");
+  if (n_neighbors > KNN_MAX_K) return fail(B2D_ERR_UNSUPPORTED, "n_neighbors > 64 is not supported");
+  if (m == 0) return B2D_OK;
+  if (k == 0) return fail(B2D_ERR_INVALID_ARG, "k must be positive");
+  if (k > 320) return fail(B2D_ERR_UNSUPPORTED, "kNN supports k <= 320 (see DESIGN.md section 3)");
+  if (!out_idx || !out_dist || !x || !y) return fail(B2D_ERR_INVALID_ARG, "null out / x / y");
+  if (ldx < k || ldy < k) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than k");
+  if (n > 0xFFFFFFFFll) return fail(B2D_ERR_INVALID_ARG, "index range exceeds 32 bits");
+  const size_t need = b2d_knn_l2_workspace_bytes(m, n, k, n_neighbors);
+  if (!workspace || workspace_bytes < need)
+    return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+  KnnCtx c;
+  c.s   = s;
+  c.w   = tc_layout(workspace, m, n, k, true);
+  c.k   = k;
+  c.nkb = static_cast<int>((k + 31) / 32);
+  c.kk  = static_cast<int>(n_neighbors);
+  c.topk     = reinterpret_cast<long long*>(static_cast<char*>(workspace) + knn_topk_offset(m, n, k));
+  c.thr      = reinterpret_cast<float*>(c.w.aux);          // [m] floats ...
+  c.cnt      = reinterpret_cast<unsigned*>(c.w.aux) + m;   // ... and [m] counters share the aux block (8 B per row)
+  c.overflow = c.w.cand_cnt;
+  int rc = launch_prep<float>(s, c.w, x, ldx, 1, m, y, ldy, 1, n, k, nullptr, nullptr, PREP_L2, 0);
+  if (rc) return rc;
+  const int64_t total = m * n_neighbors;
+  knn_init_kernel<<<static_cast<unsigned>((std::max<int64_t>(total, m) + 255) / 256), 256, 0, s>>>(c.topk, c.thr, c.cnt, c.overflow, m, c.kk);
+  B2D_CUDA(cudaGetLastError());
+  memset(&c.p, 0, sizeof(c.p));
+  c.p.m = m;
+  c.p.knn_thr = c.thr; c.p.knn_cnt = c.cnt; c.p.knn_cand = reinterpret_cast<long long*>(c.w.cand);
+  c.p.knn_cap = KNN_CAP; c.p.knn_overflow = c.overflow;
+  // pass widths KNN_CAP, KNN_CAP, 2 KNN_CAP, 4 KNN_CAP, ...: with the k-th best of the s columns seen so far as
+  // threshold, a pass over the next s columns appends ~n_neighbors entries per row on unordered data
+  int64_t off = 0;
+  while (off < n) {
+    const int64_t width = std::min<int64_t>(off == 0 ? KNN_CAP : off, n - off);
+    rc = knn_pass(c, off, width);
+    if (rc) return rc;
+    off += width;
+  }
+  knn_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(out_idx, out_dist, c.topk, total, do_sqrt);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }

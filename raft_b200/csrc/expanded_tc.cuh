@@ -64,7 +64,7 @@ constexpr int TC_MAX_STAGES  = 6;
 constexpr int TC_EPI_WARPS   = 8;
 constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
 
-enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1 };
+enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1, EPI_TOPK = 2 };
 enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
 
 struct TcParams {
@@ -90,6 +90,12 @@ struct TcParams {
   long long* keys;        // [m] packed (ordered bits of the distance << 32 | index)
   int64_t idx_offset;
   const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
+  // EPI_TOPK (fused brute-force kNN): every pair at or below the row's current k-th best joins the row's list
+  const float* knn_thr;   // [m] current k-th best squared distance of the row (+inf until k are known)
+  unsigned* knn_cnt;      // [m] fill counter of the row's candidate list
+  long long* knn_cand;    // [m][knn_cap] packed (ordered bits of the distance << 32 | index)
+  unsigned knn_cap;
+  unsigned* knn_overflow; // [1] set when a row's list is full (the pass is then repeated in halves)
 };
 
 constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES_RES * TC_A_BYTES;  // 224 KB
@@ -456,6 +462,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (row0 + 8 * j < p.m) {
               if (kEpi != EPI_STORE || p.acc_mode < 2) rv = __ldg(&p.xt[row0 + 8 * j]);
               xnr[j] = rv;
+              if (kEpi == EPI_TOPK) thr[j] = __ldg(&p.knn_thr[row0 + 8 * j]);
               if (kEpi == EPI_MINLOC) {
                 const long long ck = *reinterpret_cast<volatile long long*>(&p.keys[row0 + 8 * j]);
                 const int sb       = static_cast<int>(ck >> 32);
@@ -635,6 +642,25 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     const long long key = (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
                     atomicMin(&p.keys[row0 + 8 * j], key);
                     thr[j] = dv;
+                  } else {
+                    // EPI_TOPK: everything at or below the row's k-th best so far goes to the row's list
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                      for (int e = 0; e < 2; ++e) {
+                        const float lv = v[4 * i + o + e];
+                        const float dv = lv + xnr[j];
+                        if (dv <= thr[j] && lv < inf) {
+                          const int64_t row   = row0 + 8 * j;
+                          const unsigned slot = atomicAdd(&p.knn_cnt[row], 1u);
+                          const long long gj  = static_cast<long long>(n_blk) * TC_BN + cl0 + 8 * i + e + p.idx_offset;
+                          if (slot < p.knn_cap)
+                            p.knn_cand[row * p.knn_cap + slot] =
+                              (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
+                          else
+                            *p.knn_overflow = 1u;
+                        }
+                      }
                   }
                 }
               }
@@ -776,6 +802,84 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(long long* keys, const in
       atomicMin(&keys[ij.x], key);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused brute-force kNN: the distance tiles are never written.  The database is
+// swept in passes of doubling width; EPI_TOPK appends every pair at or below the row's current k-th
+// best to the row's list (~k per row and pass on unordered data), knn_merge_kernel folds the list
+// into the row's sorted top-k and publishes the new k-th best.
+
+constexpr int KNN_MAX_K = 64;
+constexpr int KNN_CAP   = 128;   // list entries per row and pass
+constexpr int KNN_SORT  = 256;   // KNN_MAX_K + KNN_CAP padded to a power of two
+
+__global__ void knn_init_kernel(long long* topk, float* thr, unsigned* cnt, unsigned* overflow, int64_t m, int kk)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0) *overflow = 0u;
+  if (i < m) { thr[i] = __int_as_float(0x7f800000); cnt[i] = 0u; }
+  if (i < m * kk) topk[i] = 0x7FFFFFFFFFFFFFFFll;
+}
+
+// drop the lists of a pass that overflowed (it is repeated in halves)
+__global__ void knn_reset_kernel(unsigned* cnt, unsigned* overflow, int64_t m)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0) *overflow = 0u;
+  if (i < m) cnt[i] = 0u;
+}
+
+// one warp per row: sort (top-k so far) + (this pass's list) by (distance, index), keep the first kk
+__global__ void __launch_bounds__(256) knn_merge_kernel(long long* topk, const long long* cand, unsigned* cnt, float* thr,
+                                                        int64_t m, int kk)
+{
+  __shared__ long long buf[8][KNN_SORT];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + wid;
+  if (row >= m) return;
+  const unsigned nc = min(cnt[row], static_cast<unsigned>(KNN_CAP));
+  if (nc == 0u) return;  // nothing new for this row (the common case in the late passes)
+  long long* b = buf[wid];
+  for (int t = lane; t < KNN_SORT; t += 32) {
+    long long key = 0x7FFFFFFFFFFFFFFFll;
+    if (t < kk) key = topk[row * kk + t];
+    else if (t - kk < static_cast<int>(nc)) key = cand[row * KNN_CAP + (t - kk)];
+    b[t] = key;
+  }
+  __syncwarp();
+  for (int size = 2; size <= KNN_SORT; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < KNN_SORT / 2; t += 32) {
+        const int i = 2 * t - (t & (stride - 1)), j = i + stride;
+        const bool up = (i & size) == 0;
+        const long long a = b[i], c = b[j];
+        if ((a > c) == up) { b[i] = c; b[j] = a; }
+      }
+      __syncwarp();
+    }
+  for (int t = lane; t < kk; t += 32) topk[row * kk + t] = b[t];
+  if (lane == 0) {
+    cnt[row]            = 0u;
+    const long long kth = b[kk - 1];
+    if (kth != 0x7FFFFFFFFFFFFFFFll) {
+      const int sb = static_cast<int>(kth >> 32);
+      thr[row]     = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
+    }
+  }
+}
+
+// sorted packed keys -> (index, distance) arrays: clamp at 0, optional sqrt
+__global__ void knn_finalize_kernel(int64_t* out_idx, float* out_dist, const long long* topk, int64_t total, int do_sqrt)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long key = topk[i];
+  const int s         = static_cast<int>(key >> 32);
+  float d             = fmaxf(__int_as_float(s < 0 ? (s ^ 0x7FFFFFFF) : s), 0.f);
+  if (do_sqrt) d = sqrtf(d);
+  out_idx[i]  = key == 0x7FFFFFFFFFFFFFFFll ? -1 : static_cast<int64_t>(key & 0xFFFFFFFFll);
+  out_dist[i] = key == 0x7FFFFFFFFFFFFFFFll ? __int_as_float(0x7f800000) : d;
 }
 
 }  // namespace b2d

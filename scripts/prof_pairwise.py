@@ -10,6 +10,10 @@ x = torch.randn(m, k, device="cuda", generator=g) * 3
 y = torch.randn(n, k, device="cuda", generator=g) * 3
 if what == "nn":
     fn = lambda: fused_l2_nn(x, y, sqrt=False, handle=h)
+elif what.startswith("knn"):   # knn<neighbours>, e.g. knn16: x = queries, y = dataset
+    from raft_b200.neighbors import brute_force
+    kk = int(what[3:] or 10)
+    fn = lambda: brute_force.knn(y, x, k=kk, handle=h)
 else:
     out = torch.empty(m, n, device="cuda")
     fn = lambda: pairwise_distance(x, y, out=out, metric=what, handle=h)

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include <raft/distance/fused_l2_nn.cuh>
+#include <raft/neighbors/brute_force.cuh>
 
 int main()
 {
@@ -70,6 +71,24 @@ int main()
         if (c < bv) { bv = c; best = j; }
       }
       if (hc[i].key != best || std::fabs(hc[i].value - bv) > 1e-4 * std::fmax(std::fabs(bv), 1e-2)) ++bad;
+    }
+    // brute_force::knn (k = 3): first neighbour == the fused arg-min, distances ascending
+    {
+      long long* ki; float* kd;
+      cudaMalloc(&ki, m * 3 * 8); cudaMalloc(&kd, m * 3 * 4);
+      raft::neighbors::brute_force::knn<float, int64_t>(
+        handle, raft::make_device_matrix_view<const float, int64_t>(y, (int64_t)n, (int64_t)k),
+        raft::make_device_matrix_view<const float, int64_t>(x, (int64_t)m, (int64_t)k),
+        raft::make_device_matrix_view<int64_t, int64_t>(reinterpret_cast<int64_t*>(ki), (int64_t)m, (int64_t)3),
+        raft::make_device_matrix_view<float, int64_t>(kd, (int64_t)m, (int64_t)3), raft::distance::DistanceType::L2Expanded);
+      raft::resource::sync_stream(handle);
+      std::vector<long long> hki(m * 3);
+      std::vector<float> hkd(m * 3);
+      cudaMemcpy(hki.data(), ki, m * 3 * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hkd.data(), kd, m * 3 * 4, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < m; ++i)
+        if (hki[3 * i] != hn[i].key || hkd[3 * i] > hkd[3 * i + 1] || hkd[3 * i + 1] > hkd[3 * i + 2]) ++bad;
+      cudaFree(ki); cudaFree(kd);
     }
     // error convention: unsupported metric -> raft::logic_error
     bool threw = false;

@@ -115,3 +115,19 @@ def test_make_blobs_distribution():
     assert x.dtype == np.float32 and c.shape == (5, 8) and np.abs(c).max() <= 10
     resid = x - c[lab]
     assert abs(resid.std() - 1.0) < 0.02 and abs(resid.mean()) < 0.02
+
+
+def test_knn_oracle_against_brute_force_sort():
+    """oracle.knn_l2 (blocked, lexsort by (distance, index)) == full sort of the fp64 distance matrix."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((37, 9))
+    y = rng.standard_normal((211, 9))
+    y[[50, 120]] = y[7]                                    # ties -> ascending index
+    d = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    order = np.lexsort((np.broadcast_to(np.arange(211), d.shape), d), axis=1)[:, :13]
+    gi, gv = oracle.knn_l2(x, y, 13, block=64)
+    assert (gi == order).all()
+    assert np.allclose(gv, np.take_along_axis(d, order, axis=1), rtol=1e-12, atol=1e-12)
+    gi1, gv1 = oracle.knn_l2(x, y, 1)
+    ni, nv = oracle.fused_l2_nn(x, y)
+    assert (gi1[:, 0] == ni).all() and np.allclose(gv1[:, 0], nv)
