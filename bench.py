@@ -254,6 +254,10 @@ def run_pairwise_1gpu(args):
             "hbm_gbs": (8.0 * m3 * k3 + 4.0 * m3 * m3) / (ms_o * 1e-3) / 1e9,
             "fp32_lane_ops_per_s": 2.0 * m3 * m3 * k3 / (ms_o * 1e-3), "bound": "fp32 pipe (148 SMs x 128 lanes x clk)"}
     del x3, y3
+    # fused brute-force kNN: top-16 of every row of the 100000x100000x128 problem, matrix never written
+    from raft_b200.neighbors import brute_force
+    ms_o = t_ms(lambda: brute_force.knn(y, x, k=16, handle=h), steps=2)
+    others["kNN k=16 100000x100000x128 f32 (fused select)"] = {"ms": ms_o, "pairs_per_s": pairs / (ms_o * 1e-3)}
     # fp16-in / fp32-accumulate 200000x200000x64: the 160 GB result is produced in 4 row blocks into a reused buffer
     m5, k5, blk = 200_000, 64, 50_000
     c5 = centers_device(k5, torch, dev)

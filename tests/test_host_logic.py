@@ -98,6 +98,18 @@ WORKER = textwrap.dedent('''
     assert (idx == ref_idx).all(), (rank, np.nonzero(idx != ref_idx))
     assert idx[0] == 3
     assert np.allclose(np.maximum(val.astype(np.float64), 0), ref_val, rtol=1e-4, atol=1e-3)
+    # the two-exchange form of fused_l2_nn_sharded: head of every shard, all-reduce (global bounds),
+    # the rest of the shard continuing from the reduced keys (init_keys = 0 == elementwise MIN), all-reduce
+    head = 100
+    def shard_keys(a, b):
+        dd = oracle.pairwise_distance(x, y[a:b], oracle.DistanceType.L2Expanded)
+        ll = np.argmin(dd, axis=1)
+        return torch.from_numpy(oracle.pack_minloc(dd[np.arange(len(x)), ll].astype(np.float32), ll + a))
+    k2 = shard_keys(lo, lo + head)
+    dist.all_reduce(k2, op=dist.ReduceOp.MIN)
+    k2 = torch.minimum(k2, shard_keys(lo + head, hi))
+    dist.all_reduce(k2, op=dist.ReduceOp.MIN)
+    assert torch.equal(k2, keys)
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 ''')
