@@ -139,6 +139,17 @@ int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, 
                int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, int do_sqrt,
                void* workspace, size_t workspace_bytes);
 
+/* raft::stats::silhouette_score (cpp/include/raft/stats/detail/silhouette_score.cuh:186-328), a caller of
+ * the distance path: *score (device) = mean over samples of (b - a) / max(a, b);
+ * per_sample (device, [n]) optional.  labels: int32 in [0, n_labels).  metric: any metric of
+ * b2d_pairwise_distance (the reference's default is L2Unexpanded).  The n x n matrix is produced and
+ * consumed in [chunk_rows x n] slabs (0 = about 1 GiB per slab), like the reference's batched variant
+ * (detail/batched/silhouette_score.cuh:213-243).  Synchronises the stream once (label validation). */
+size_t b2d_silhouette_score_workspace_bytes(int64_t n, int64_t k, int n_labels, int metric, int64_t chunk_rows);
+int b2d_silhouette_score(void* stream, float* score, float* per_sample, const float* x, int64_t ldx,
+                         const int* labels, int64_t n, int64_t k, int n_labels, int metric, float metric_arg,
+                         int64_t chunk_rows, void* workspace, size_t workspace_bytes);
+
 /* out[r] = norm of row r of x:[rows,k] (L2Norm = sum of squares; do_sqrt applies sqrt_op as
  * fin_op, cpp/include/raft/linalg/norm.cuh:118-147). */
 int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k,

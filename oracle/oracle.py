@@ -12,7 +12,7 @@ import numpy as np
 __all__ = [
     "DistanceType", "pairwise_distance", "fused_l2_nn", "row_norm_sq", "argmin_op",
     "row_argmin", "compare_approx", "match_approx", "make_blobs", "EXPANDED", "UNEXPANDED",
-    "pack_minloc", "unpack_minloc", "knn_l2",
+    "pack_minloc", "unpack_minloc", "knn_l2", "silhouette_score",
 ]
 
 
@@ -207,6 +207,30 @@ def knn_l2(x, y, n_neighbors: int, sqrt: bool = False, block: int = 4096):
     if sqrt:
         best_v = np.sqrt(best_v)
     return best_i, best_v
+
+
+def silhouette_score(x, labels, n_labels=None, metric=None, metric_arg=2.0, return_samples=False):
+    """Mean silhouette coefficient, restating raft::stats::silhouette_score
+    (cpp/include/raft/stats/detail/silhouette_score.cuh:186-328; per-sample rule SilOp :155-167,
+    singleton rule populateAKernel :72-84): a = mean distance to the OTHER members of the own cluster,
+    b = min over the other non-empty clusters of the mean distance to it, s = 0 for singleton clusters
+    or a == b, else (b - a) / max(a, b).  Default metric = the reference's (L2Unexpanded, squared)."""
+    metric = DistanceType.L2Unexpanded if metric is None else metric
+    labels = np.asarray(labels)
+    n = len(labels)
+    n_labels = int(labels.max()) + 1 if n_labels is None else int(n_labels)
+    d = pairwise_distance(x, x, metric, metric_arg)
+    counts = np.bincount(labels, minlength=n_labels).astype(np.float64)
+    sums = np.zeros((n, n_labels))
+    for c in range(n_labels):
+        sums[:, c] = d[:, labels == c].sum(axis=1)
+    own = labels
+    a = np.where(counts[own] > 1, sums[np.arange(n), own] / np.maximum(counts[own] - 1, 1), -1.0)
+    mean = np.where(counts[None, :] > 0, sums / np.maximum(counts[None, :], 1), np.inf)
+    mean[np.arange(n), own] = np.inf
+    b = mean.min(axis=1)
+    s = np.where((a == -1.0) | (a == b), 0.0, np.where(a > b, (b - a) / np.where(a == 0, 1, a), (b - a) / np.where(b == 0, 1, b)))
+    return (float(s.mean()), s) if return_samples else float(s.mean())
 
 
 def compare_approx(a, b, eps):

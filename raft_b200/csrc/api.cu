@@ -13,6 +13,7 @@
 #include "screen_tc.cuh"
 #include "prep.cuh"
 #include "unexpanded_simt.cuh"
+#include "stats.cuh"
 
 namespace b2d {
 
@@ -769,6 +770,96 @@ int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, 
     off += width;
   }
   knn_finalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(out_idx, out_dist, c.topk, total, do_sqrt);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// raft::stats::silhouette_score on the distance engine (stats.cuh)
+
+namespace {
+struct SilLayout {
+  size_t counts, offsets, cursor, bad, total, where, ys, slab, pw, bytes;
+  int64_t chunk, ld;
+  size_t pw_bytes;
+};
+SilLayout sil_layout(int64_t n, int64_t k, int n_labels, int metric, int64_t chunk_rows)
+{
+  SilLayout L;
+  L.ld = (n + 3) / 4 * 4;
+  int64_t c = chunk_rows > 0 ? chunk_rows : (int64_t(1) << 30) / (4 * std::max<int64_t>(L.ld, 1));
+  c         = std::max<int64_t>(128, c / 128 * 128);
+  L.chunk   = std::min<int64_t>(c, std::max<int64_t>(n, 1));
+  size_t off = 0;
+  auto take  = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
+  L.counts  = take(static_cast<size_t>(n_labels) * 4);
+  L.offsets = take(static_cast<size_t>(n_labels + 1) * 4);
+  L.cursor  = take(static_cast<size_t>(n_labels) * 4);
+  L.bad     = take(4);
+  L.total   = take(8);
+  L.where   = take(static_cast<size_t>(n) * 4);
+  L.ys      = take(static_cast<size_t>(n) * k * 4);
+  L.slab    = take(static_cast<size_t>(L.chunk) * L.ld * 4);
+  L.pw_bytes = b2d_pairwise_workspace_bytes(metric, B2D_F32, L.chunk, n, k);
+  L.pw      = take(L.pw_bytes == static_cast<size_t>(-1) ? 0 : L.pw_bytes);
+  L.bytes   = off;
+  return L;
+}
+}  // namespace
+
+size_t b2d_silhouette_score_workspace_bytes(int64_t n, int64_t k, int n_labels, int metric, int64_t chunk_rows)
+{
+  if (n < 0 || k < 0 || n_labels < 1 || chunk_rows < 0) return static_cast<size_t>(-1);
+  if (b2d_pairwise_workspace_bytes(metric, B2D_F32, 1, 1, k) == static_cast<size_t>(-1)) return static_cast<size_t>(-1);
+  return sil_layout(n, k, n_labels, metric, chunk_rows).bytes;
+}
+
+int b2d_silhouette_score(void* stream, float* score, float* per_sample, const float* x, int64_t ldx, const int* labels,
+                         int64_t n, int64_t k, int n_labels, int metric, float metric_arg, int64_t chunk_rows,
+                         void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n < 0 || k <= 0 || chunk_rows < 0) return fail(B2D_ERR_INVALID_ARG, "bad extent");
+  if (!score || !x || !labels) return fail(B2D_ERR_INVALID_ARG, "null score / x / labels");
+  if (n_labels < 2 || n_labels > n - 1)
+    return fail(B2D_ERR_INVALID_ARG, "silhouette score is not defined for this number of labels (need 2 <= n_labels <= n - 1)");
+  if (n_labels > 12000) return fail(B2D_ERR_UNSUPPORTED, "n_labels > 12000");
+  if (ldx < k) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than k");
+  const size_t need = b2d_silhouette_score_workspace_bytes(n, k, n_labels, metric, chunk_rows);
+  if (need == static_cast<size_t>(-1)) return fail(B2D_ERR_UNSUPPORTED, "metric " + std::to_string(metric) + " is not on the B200 distance path");
+  if (!workspace || workspace_bytes < need)
+    return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+  const SilLayout L = sil_layout(n, k, n_labels, metric, chunk_rows);
+  char* base    = static_cast<char*>(workspace);
+  int* counts   = reinterpret_cast<int*>(base + L.counts);
+  int* offsets  = reinterpret_cast<int*>(base + L.offsets);
+  int* cursor   = reinterpret_cast<int*>(base + L.cursor);
+  unsigned* bad = reinterpret_cast<unsigned*>(base + L.bad);
+  double* total = reinterpret_cast<double*>(base + L.total);
+  int* where    = reinterpret_cast<int*>(base + L.where);
+  float* ys     = reinterpret_cast<float*>(base + L.ys);
+  float* slab   = reinterpret_cast<float*>(base + L.slab);
+  B2D_CUDA(cudaMemsetAsync(base, 0, L.where, s));  // counts, offsets, cursor, bad, total
+  const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+  sil_count_kernel<<<nb, 256, 0, s>>>(labels, counts, n, n_labels, bad);
+  sil_scan_kernel<<<1, 32, 0, s>>>(counts, offsets, cursor, n_labels);
+  sil_gather_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(x, ldx, labels, cursor, ys, where, n, static_cast<int>(k), n_labels);
+  B2D_CUDA(cudaGetLastError());
+  unsigned h_bad = 0;
+  B2D_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
+  B2D_CUDA(cudaStreamSynchronize(s));
+  if (h_bad) return fail(B2D_ERR_INVALID_ARG, "labels must lie in [0, n_labels)");
+  for (int64_t r0 = 0; r0 < n; r0 += L.chunk) {
+    const int64_t rows = std::min<int64_t>(L.chunk, n - r0);
+    int rc = b2d_pairwise_distance(stream, metric, B2D_F32, x + r0 * ldx, ldx, ys, k, slab, L.ld, rows, n, k, 1, metric_arg,
+                                   base + L.pw, L.pw_bytes);
+    if (rc) return rc;
+    sil_row_kernel<<<static_cast<unsigned>(rows), 256, static_cast<size_t>(n_labels) * 4, s>>>(
+      slab, L.ld, r0, rows, labels, counts, offsets, where, n_labels, per_sample, total);
+    B2D_CUDA(cudaGetLastError());
+  }
+  sil_finish_kernel<<<1, 32, 0, s>>>(total, score, n);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }

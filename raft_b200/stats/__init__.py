@@ -1,0 +1,47 @@
+"""Callers of the distance path: ``silhouette_score`` on the raft_b200 engine -- the
+role of ``raft::stats::silhouette_score`` (cpp/include/raft/stats/silhouette_score.cuh), whose call into
+``raft::distance::pairwise_distance`` is dangling in the reference snapshot
+(cpp/include/raft/stats/detail/silhouette_score.cuh:205-206)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..common import auto_sync_handle, cai_wrapper
+from ..distance.distance_type import resolve_metric
+
+
+@auto_sync_handle
+def silhouette_score(X, labels, n_labels=None, metric="sqeuclidean_unexpanded", p=2.0, chunk=0, return_samples=False,
+                     handle=None):
+    """Mean silhouette coefficient of the samples X [n, d] (float32, C-contiguous, on the device) under the
+    clustering ``labels`` (int32 in [0, n_labels)).  ``metric`` takes the names of ``pairwise_distance``;
+    the default is the reference's (DistanceType::L2Unexpanded, i.e. squared Euclidean) -- pass
+    "euclidean" for scikit-learn's default.  ``chunk``: rows of the distance matrix alive at a time
+    (0: about 1 GiB).  Returns a float, or (float, per-sample scores [n]) with ``return_samples``."""
+    x_cai, l_cai = cai_wrapper(X), cai_wrapper(labels)
+    x_cai.validate_shape_dtype(expected_dims=2, expected_dtype=np.float32)
+    l_cai.validate_shape_dtype(expected_dims=1, expected_dtype=np.int32)
+    if not x_cai.c_contiguous:
+        raise ValueError("Inputs must be C contiguous")
+    n, d = x_cai.shape
+    if l_cai.shape[0] != n:
+        raise ValueError("labels must have one entry per sample")
+    if n_labels is None:
+        n_labels = int(torch.as_tensor(labels, device=handle.device).max().item()) + 1
+    mt = int(resolve_metric(metric))
+    L = _lib.lib()
+    need = L.b2d_silhouette_score_workspace_bytes(n, d, int(n_labels), mt, int(chunk))
+    if need == 2 ** 64 - 1:
+        raise _lib.LogicError("metric %s is not supported" % metric)
+    ws = handle.workspace(need)
+    with torch.cuda.stream(handle.torch_stream):
+        score = torch.empty(1, dtype=torch.float32, device=handle.device)
+        per = torch.empty(n, dtype=torch.float32, device=handle.device) if return_samples else None
+    _lib.check(L.b2d_silhouette_score(handle.stream_ptr, score.data_ptr(), per.data_ptr() if per is not None else None,
+                                      x_cai.data, d, l_cai.data, n, d, int(n_labels), mt, float(p), int(chunk),
+                                      ws.data_ptr(), ws.numel()))
+    handle.sync()
+    val = float(score.item())
+    return (val, per) if return_samples else val

@@ -1,0 +1,12 @@
+import sys, time, torch
+sys.path.insert(0, ".")
+from raft_b200.stats import silhouette_score
+from raft_b200.common import DeviceResources
+h = DeviceResources()
+n, k, nl = 100000, 128, 10
+lab = torch.randint(0, nl, (n,), device="cuda", dtype=torch.int32)
+x = torch.randn(n, k, device="cuda") + lab[:, None].float()
+for metric in ("sqeuclidean", "euclidean", "sqeuclidean_unexpanded", "cosine"):
+    silhouette_score(x, lab, nl, metric=metric, handle=h); torch.cuda.synchronize()
+    t = time.perf_counter(); v = silhouette_score(x, lab, nl, metric=metric, handle=h); torch.cuda.synchronize()
+    print(f"silhouette {n}x{k}, {nl} labels, {metric}: {(time.perf_counter()-t)*1e3:.1f} ms  score {v:.4f}")

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <raft/distance/fused_l2_nn.cuh>
 #include <raft/neighbors/brute_force.cuh>
+#include <raft/stats/silhouette_score.cuh>
 
 int main()
 {
@@ -89,6 +90,28 @@ int main()
       for (int i = 0; i < m; ++i)
         if (hki[3 * i] != hn[i].key || hkd[3 * i] > hkd[3 * i + 1] || hkd[3 * i + 1] > hkd[3 * i + 2]) ++bad;
       cudaFree(ki); cudaFree(kd);
+    }
+    // raft::stats::silhouette_score (reference signature; default metric L2Unexpanded) vs a host loop
+    {
+      std::vector<int> hl(m);
+      for (int i = 0; i < m; ++i) hl[i] = (i * 7 + i / 13) % 3;
+      int* dl; cudaMalloc(&dl, m * 4); cudaMemcpy(dl, hl.data(), m * 4, cudaMemcpyHostToDevice);
+      const float sc = raft::stats::silhouette_score<float, int>(handle, x, m, k, dl, 3, nullptr, s);
+      double tot = 0;
+      for (int i = 0; i < m; ++i) {
+        double sum[3] = {0, 0, 0}; int cnt[3] = {0, 0, 0};
+        for (int j = 0; j < m; ++j) {
+          double acc = 0;
+          for (int t = 0; t < k; ++t) { double df = (double)hx[i * k + t] - hx[j * k + t]; acc += df * df; }
+          sum[hl[j]] += acc; ++cnt[hl[j]];
+        }
+        const double a = sum[hl[i]] / (cnt[hl[i]] - 1);
+        double b = 1e300;
+        for (int c = 0; c < 3; ++c) if (c != hl[i]) b = std::fmin(b, sum[c] / cnt[c]);
+        tot += (b - a) / std::fmax(a, b);
+      }
+      if (std::fabs(sc - tot / m) > 2e-4) { std::printf("silhouette %f vs %f\n", sc, tot / m); ++bad; }
+      cudaFree(dl);
     }
     // error convention: unsupported metric -> raft::logic_error
     bool threw = false;

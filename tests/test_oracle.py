@@ -131,3 +131,20 @@ def test_knn_oracle_against_brute_force_sort():
     gi1, gv1 = oracle.knn_l2(x, y, 1)
     ni, nv = oracle.fused_l2_nn(x, y)
     assert (gi1[:, 0] == ni).all() and np.allclose(gv1[:, 0], nv)
+
+
+def test_silhouette_oracle_pinned_to_sklearn():
+    """The silhouette restatement against scikit-learn's implementation (an independent pin: same
+    definition as raft::stats::silhouette_score, incl. score 0 for singleton clusters)."""
+    skm = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((300, 7)) + rng.integers(0, 4, 300)[:, None] * 2.5
+    labels = rng.integers(0, 5, 300)
+    labels[labels == 4] = 3
+    labels[0] = 4                                           # a singleton cluster
+    for metric, sk in ((oracle.DistanceType.L2SqrtUnexpanded, "euclidean"), (oracle.DistanceType.L2Unexpanded, "sqeuclidean"),
+                       (oracle.DistanceType.L1, "cityblock"), (oracle.DistanceType.CosineExpanded, "cosine")):
+        got, per = oracle.silhouette_score(x, labels, metric=metric, return_samples=True)
+        assert abs(got - skm.silhouette_score(x, labels, metric=sk)) < 1e-9
+        assert np.allclose(per, skm.silhouette_samples(x, labels, metric=sk), atol=1e-9)
+        assert per[0] == 0.0
