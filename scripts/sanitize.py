@@ -1,0 +1,26 @@
+"""Small run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+   compute-sanitizer --tool memcheck python scripts/sanitize.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from raft_b200.distance import pairwise_distance, fused_l2_nn, fused_distance_nn
+from raft_b200.neighbors import brute_force
+from raft_b200.stats import silhouette_score
+g = torch.Generator(device="cuda").manual_seed(0)
+r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+x, y = r(300, 96), r(20000, 96)
+i, v = fused_l2_nn(x, y, sqrt=False)                       # screened search: sample / trial / main / exact
+print("nn screened", int(i.sum()), float(v.sum()))
+i, v = fused_l2_nn(r(300, 40), r(700, 40))                 # exact kernel only
+i, v = fused_distance_nn(r(130, 200), r(300, 200), metric="cosine")   # streaming (k > 128) arg-min
+d = pairwise_distance(r(257, 100), r(515, 100), metric="sqeuclidean")  # TMA-store epilogue? n % 4 != 0 -> direct
+d = pairwise_distance(r(256, 128), r(512, 128), metric="euclidean")    # TMA-store epilogue
+d = pairwise_distance(r(100, 700), r(90, 700), metric="sqeuclidean")   # K-chunked
+d = pairwise_distance(r(130, 33), r(70, 33), metric="cityblock")       # SIMT loader
+d = pairwise_distance(r(128, 64), r(256, 64), metric="chebyshev")      # TMA-fed FP32 kernel
+dd, ii = brute_force.knn(r(3000, 32), r(200, 32), k=8)
+print("knn", int(ii.sum()))
+lab = torch.randint(0, 4, (500,), device="cuda", dtype=torch.int32, generator=g)
+print("silhouette", silhouette_score(r(500, 16), lab, 4))
+torch.cuda.synchronize()
+print("done")
