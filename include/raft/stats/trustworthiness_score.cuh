@@ -1,0 +1,26 @@
+// raft::stats::trustworthiness_score -- shim over b2d_trustworthiness_score (include/raft_b200.h).
+// Pointer signature of cpp/include/raft/stats/trustworthiness_score.cuh:29-41 (its pairwise_distance
+// call, detail/trustworthiness_score.cuh:152-153, dangles in the reference snapshot).
+#pragma once
+#include "../distance/distance.cuh"
+
+namespace raft {
+namespace stats {
+
+template <typename math_t, raft::distance::DistanceType distance_type>
+double trustworthiness_score(const raft::resources& h, const math_t* X, math_t* X_embedded, int n, int m, int d,
+                             int n_neighbors, int batchSize = 512)
+{
+  static_assert(std::is_same<math_t, float>::value, "raft_b200: trustworthiness_score is provided for float");
+  const size_t need = b2d_trustworthiness_score_workspace_bytes(n, m, d, n_neighbors, static_cast<int>(distance_type), batchSize);
+  if (need == static_cast<size_t>(-1)) throw raft::logic_error("trustworthiness_score: unsupported n_neighbors / metric");
+  void* ws     = h.workspace(need);
+  double score = 0.0;
+  raft::distance::detail::b2d_check(b2d_trustworthiness_score(raft::resource::get_cuda_stream(h), &score, X, m, X_embedded,
+                                                              d, n, m, d, n_neighbors, static_cast<int>(distance_type),
+                                                              batchSize, ws, need));
+  return score;
+}
+
+}  // namespace stats
+}  // namespace raft

@@ -150,6 +150,18 @@ int b2d_silhouette_score(void* stream, float* score, float* per_sample, const fl
                          const int* labels, int64_t n, int64_t k, int n_labels, int metric, float metric_arg,
                          int64_t chunk_rows, void* workspace, size_t workspace_bytes);
 
+/* raft::stats::trustworthiness_score (cpp/include/raft/stats/detail/trustworthiness_score.cuh:113-211), the
+ * other dangling caller: x [n, m] original space, x_embedded [n, d]; neighbours in the
+ * embedded space from the fused kNN (L2), ranks in the original space (`metric`: any metric of
+ * b2d_pairwise_distance) counted over [batch_rows x n] slabs (0 = about 1 GiB).  *score_host is a HOST
+ * double; the call synchronises the stream.  n_neighbors <= 63. */
+size_t b2d_trustworthiness_score_workspace_bytes(int64_t n, int64_t m, int64_t d, int n_neighbors, int metric,
+                                                 int64_t batch_rows);
+int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, int64_t ldx,
+                              const float* x_embedded, int64_t lde, int64_t n, int64_t m, int64_t d,
+                              int n_neighbors, int metric, int64_t batch_rows, void* workspace,
+                              size_t workspace_bytes);
+
 /* out[r] = norm of row r of x:[rows,k] (L2Norm = sum of squares; do_sqrt applies sqrt_op as
  * fin_op, cpp/include/raft/linalg/norm.cuh:118-147). */
 int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k,

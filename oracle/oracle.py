@@ -12,7 +12,7 @@ import numpy as np
 __all__ = [
     "DistanceType", "pairwise_distance", "fused_l2_nn", "row_norm_sq", "argmin_op",
     "row_argmin", "compare_approx", "match_approx", "make_blobs", "EXPANDED", "UNEXPANDED",
-    "pack_minloc", "unpack_minloc", "knn_l2", "silhouette_score",
+    "pack_minloc", "unpack_minloc", "knn_l2", "silhouette_score", "trustworthiness_score",
 ]
 
 
@@ -231,6 +231,30 @@ def silhouette_score(x, labels, n_labels=None, metric=None, metric_arg=2.0, retu
     b = mean.min(axis=1)
     s = np.where((a == -1.0) | (a == b), 0.0, np.where(a > b, (b - a) / np.where(a == 0, 1, a), (b - a) / np.where(b == 0, 1, b)))
     return (float(s.mean()), s) if return_samples else float(s.mean())
+
+
+def trustworthiness_score(x, x_embedded, n_neighbors: int = 5, metric=None):
+    """Restates raft::stats::trustworthiness_score (cpp/include/raft/stats/detail/
+    trustworthiness_score.cuh:113-211): neighbours j of i in the embedded space (n_neighbors + 1 with i
+    itself, Euclidean), r(i, j) = position of j in the order of the samples by original-space distance
+    from i (i first; ties by index), penalty max(0, r - n_neighbors).  Same value as
+    sklearn.manifold.trustworthiness."""
+    metric = DistanceType.L2SqrtUnexpanded if metric is None else metric
+    x = np.asarray(x, dtype=np.float64)
+    e = np.asarray(x_embedded, dtype=np.float64)
+    n, k = x.shape[0], int(n_neighbors)
+    d = pairwise_distance(x, x, metric, 2.0)
+    np.fill_diagonal(d, -np.inf)                                   # the sample itself comes first
+    order = np.lexsort((np.broadcast_to(np.arange(n), d.shape), d), axis=1)
+    rank = np.empty_like(order)
+    np.put_along_axis(rank, order, np.broadcast_to(np.arange(n), d.shape), axis=1)
+    nbr, _ = knn_l2(e, e, k + 1)
+    t = 0.0
+    for i in range(n):
+        for j in nbr[i]:
+            if j != i:
+                t += max(0, int(rank[i, j]) - k)
+    return 1.0 - (2.0 / ((n * k) * ((2.0 * n) - (3.0 * k) - 1.0))) * t
 
 
 def compare_approx(a, b, eps):

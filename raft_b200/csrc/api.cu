@@ -864,6 +864,87 @@ int b2d_silhouette_score(void* stream, float* score, float* per_sample, const fl
   return B2D_OK;
 }
 
+// raft::stats::trustworthiness_score on the kNN + distance engine (stats.cuh)
+namespace {
+struct TrustLayout {
+  size_t penalty, emb_idx, emb_dist, slab, scratch, bytes;
+  int64_t chunk, ld;
+  size_t knn_bytes, pw_bytes;
+};
+TrustLayout trust_layout(int64_t n, int64_t m, int64_t d, int n_neighbors, int metric, int64_t batch_rows)
+{
+  TrustLayout L;
+  L.ld = (n + 3) / 4 * 4;
+  int64_t c = batch_rows > 0 ? batch_rows : (int64_t(1) << 30) / (4 * std::max<int64_t>(L.ld, 1));
+  c         = std::max<int64_t>(128, c / 128 * 128);
+  L.chunk   = std::min<int64_t>(c, std::max<int64_t>(n, 1));
+  size_t off = 0;
+  auto take  = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
+  L.penalty  = take(8);
+  L.emb_idx  = take(static_cast<size_t>(n) * (n_neighbors + 1) * 8);
+  L.emb_dist = take(static_cast<size_t>(n) * (n_neighbors + 1) * 4);
+  L.slab     = take(static_cast<size_t>(L.chunk) * L.ld * 4);
+  L.knn_bytes = b2d_knn_l2_workspace_bytes(n, n, d, n_neighbors + 1);
+  L.pw_bytes  = b2d_pairwise_workspace_bytes(metric, B2D_F32, L.chunk, n, m);
+  const size_t a = L.knn_bytes == static_cast<size_t>(-1) ? 0 : L.knn_bytes;
+  const size_t b = L.pw_bytes == static_cast<size_t>(-1) ? 0 : L.pw_bytes;
+  L.scratch  = take(std::max(a, b));
+  L.bytes    = off;
+  return L;
+}
+}  // namespace
+
+size_t b2d_trustworthiness_score_workspace_bytes(int64_t n, int64_t m, int64_t d, int n_neighbors, int metric,
+                                                 int64_t batch_rows)
+{
+  if (n < 0 || m < 0 || d < 0 || n_neighbors < 1 || n_neighbors + 1 > KNN_MAX_K || batch_rows < 0) return static_cast<size_t>(-1);
+  if (b2d_pairwise_workspace_bytes(metric, B2D_F32, 1, 1, m) == static_cast<size_t>(-1)) return static_cast<size_t>(-1);
+  return trust_layout(n, m, d, n_neighbors, metric, batch_rows).bytes;
+}
+
+int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, int64_t ldx, const float* x_embedded,
+                              int64_t lde, int64_t n, int64_t m, int64_t d, int n_neighbors, int metric,
+                              int64_t batch_rows, void* workspace, size_t workspace_bytes)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n < 0 || m <= 0 || d <= 0 || batch_rows < 0) return fail(B2D_ERR_INVALID_ARG, "bad extent");
+  if (!score_host || !x || !x_embedded) return fail(B2D_ERR_INVALID_ARG, "null score / x / x_embedded");
+  if (n_neighbors < 1 || n_neighbors + 1 > KNN_MAX_K) return fail(B2D_ERR_UNSUPPORTED, "n_neighbors must be in [1, 63]");
+  if (2 * n - 3 * static_cast<int64_t>(n_neighbors) - 1 <= 0 || n_neighbors + 1 > n)
+    return fail(B2D_ERR_INVALID_ARG, "n_neighbors must be smaller than n / 2");
+  if (ldx < m || lde < d) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than the row length");
+  const size_t need = b2d_trustworthiness_score_workspace_bytes(n, m, d, n_neighbors, metric, batch_rows);
+  if (need == static_cast<size_t>(-1)) return fail(B2D_ERR_UNSUPPORTED, "metric " + std::to_string(metric) + " is not on the B200 distance path");
+  if (!workspace || workspace_bytes < need)
+    return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+  const TrustLayout L = trust_layout(n, m, d, n_neighbors, metric, batch_rows);
+  char* base = static_cast<char*>(workspace);
+  unsigned long long* penalty = reinterpret_cast<unsigned long long*>(base + L.penalty);
+  int64_t* emb_idx = reinterpret_cast<int64_t*>(base + L.emb_idx);
+  float* emb_dist  = reinterpret_cast<float*>(base + L.emb_dist);
+  float* slab      = reinterpret_cast<float*>(base + L.slab);
+  const int kk1    = n_neighbors + 1;
+  B2D_CUDA(cudaMemsetAsync(penalty, 0, 8, s));
+  // neighbours in the embedded space (the sample itself included, as in the reference)
+  int rc = b2d_knn_l2(stream, emb_idx, emb_dist, x_embedded, lde, x_embedded, lde, n, n, d, kk1, 0, base + L.scratch, L.knn_bytes);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n; r0 += L.chunk) {
+    const int64_t rows = std::min<int64_t>(L.chunk, n - r0);
+    rc = b2d_pairwise_distance(stream, metric, B2D_F32, x + r0 * ldx, ldx, x, ldx, slab, L.ld, rows, n, m, 1, 2.0f,
+                               base + L.scratch, L.pw_bytes);
+    if (rc) return rc;
+    trust_rank_kernel<<<static_cast<unsigned>(rows), 256, 0, s>>>(slab, L.ld, r0, n, emb_idx, kk1, n_neighbors, penalty);
+    B2D_CUDA(cudaGetLastError());
+  }
+  unsigned long long t = 0;
+  B2D_CUDA(cudaMemcpyAsync(&t, penalty, 8, cudaMemcpyDeviceToHost, s));
+  B2D_CUDA(cudaStreamSynchronize(s));
+  const double nn = static_cast<double>(n), kk = static_cast<double>(n_neighbors);
+  *score_host = 1.0 - (2.0 / ((nn * kk) * ((2.0 * nn) - (3.0 * kk) - 1.0))) * static_cast<double>(t);
+  return B2D_OK;
+}
+
 int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k, int norm_type,
                  int do_sqrt)
 {

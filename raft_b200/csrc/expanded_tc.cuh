@@ -45,6 +45,9 @@
 //                     compared with the row's current global best (read from keys at tile start:
 //                     an upper bound, keys only decrease); only a candidate that can change the
 //                     result takes the slow path (smallest-column scan + packed 64-bit atomicMin).
+//   EPI_TOPK          fused brute-force kNN: the same tree and vote against the row's current k-th best;
+//                     every pair at or below it is appended to the row's candidate list (see the kNN
+//                     helpers at the end of this file).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

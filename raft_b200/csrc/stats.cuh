@@ -1,4 +1,5 @@
-// Callers of the distance path: silhouette score on top of the pairwise engine.
+// Callers of the distance path: silhouette and trustworthiness scores on top of the
+// pairwise / kNN engine.
 //
 // Semantics follow raft::stats::silhouette_score (cpp/include/raft/stats/detail/silhouette_score.cuh:
 // 186-328): a(i) = mean distance to the other members of i's cluster (-1 marks a singleton cluster ->
@@ -92,6 +93,69 @@ __global__ void __launch_bounds__(256) sil_row_kernel(const float* slab, int64_t
 __global__ void sil_finish_kernel(const double* total, float* score, int64_t n)
 {
   if (threadIdx.x == 0 && blockIdx.x == 0) *score = static_cast<float>(*total / static_cast<double>(n));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trustworthiness (raft::stats::trustworthiness_score, cpp/include/raft/stats/detail/
+// trustworthiness_score.cuh:113-211): for every sample i and each of its n_neighbors + 1 nearest
+// neighbours j in the EMBEDDED space, r(i, j) = position of j when the samples are ordered by their
+// ORIGINAL-space distance from i (i itself first), penalty max(0, r - n_neighbors);
+// score = 1 - 2 / (n k (2n - 3k - 1)) * sum of the penalties.  The reference sorts every row of the
+// original-space distance matrix (sort_cols_per_row + a lookup table); only k + 1 ranks per row are
+// needed, so here a rank is a COUNT: the entries of the row that precede d(i, j) -- one block per row
+// of the slab, ballots over 32 columns at a time, batches that cannot precede any of the row's
+// thresholds skipped.
+__global__ void __launch_bounds__(256) trust_rank_kernel(const float* slab, int64_t ld, int64_t row0, int64_t n,
+                                                         const int64_t* emb_idx, int kk1, int n_neighbors,
+                                                         unsigned long long* penalty)
+{
+  __shared__ float thr[64];
+  __shared__ int nbr[64];
+  __shared__ unsigned cnt[64];
+  __shared__ float tmax_s;
+  const int64_t row = row0 + blockIdx.x;
+  const float* d    = slab + static_cast<int64_t>(blockIdx.x) * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x < 64) {
+    float t = __int_as_float(0xff800000);  // -inf: nothing precedes (self entries, padding)
+    int j   = -1;
+    if (threadIdx.x < kk1) {
+      const int64_t e = emb_idx[row * kk1 + threadIdx.x];
+      if (e >= 0 && e < n && e != row) { j = static_cast<int>(e); t = d[e]; }
+    }
+    thr[threadIdx.x] = t;
+    nbr[threadIdx.x] = j;
+    cnt[threadIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tm = __int_as_float(0xff800000);
+    for (int q = 0; q < kk1; ++q) tm = fmaxf(tm, thr[q]);
+    tmax_s = tm;
+  }
+  __syncthreads();
+  const float tmax = tmax_s;
+  unsigned c0 = 0, c1 = 0;  // lane q & 31 counts for neighbour q (q < 32 -> c0, else c1)
+  for (int64_t l0 = static_cast<int64_t>(warp) * 32; l0 < n; l0 += static_cast<int64_t>(nw) * 32) {
+    const int64_t l  = l0 + lane;
+    const bool valid = l < n && l != row;
+    const float v    = valid ? d[l] : 0.f;
+    if (!__any_sync(0xffffffffu, valid && v <= tmax)) continue;
+    for (int q = 0; q < kk1; ++q) {
+      const float t = thr[q];
+      const int j   = nbr[q];
+      const bool before = valid && l != j && (v < t || (v == t && l < j));
+      const unsigned b  = __ballot_sync(0xffffffffu, before);
+      if (lane == (q & 31)) { if (q < 32) c0 += __popc(b); else c1 += __popc(b); }
+    }
+  }
+  if (lane < kk1 && c0) atomicAdd(&cnt[lane], c0);
+  if (lane + 32 < kk1 && c1) atomicAdd(&cnt[lane + 32], c1);
+  __syncthreads();
+  if (threadIdx.x < kk1 && nbr[threadIdx.x] >= 0) {
+    const long long r = static_cast<long long>(cnt[threadIdx.x]) + 1;  // the sample itself comes first
+    if (r > n_neighbors) atomicAdd(penalty, static_cast<unsigned long long>(r - n_neighbors));
+  }
 }
 
 }  // namespace b2d

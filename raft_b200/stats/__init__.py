@@ -45,3 +45,34 @@ def silhouette_score(X, labels, n_labels=None, metric="sqeuclidean_unexpanded", 
     handle.sync()
     val = float(score.item())
     return (val, per) if return_samples else val
+
+
+@auto_sync_handle
+def trustworthiness_score(X, X_embedded, n_neighbors=5, metric="euclidean", batch_size=0, handle=None):
+    """Trustworthiness of the embedding ``X_embedded`` [n, d] of ``X`` [n, m] (both float32, C-contiguous, on
+    the device): 1 - 2 / (n k (2n - 3k - 1)) * sum over samples i and their k embedded-space neighbours j
+    of max(0, r(i, j) - k), r = rank of j among the original-space neighbours of i
+    (raft::stats::trustworthiness_score, cpp/include/raft/stats/trustworthiness_score.cuh:29-41; same
+    definition as sklearn.manifold.trustworthiness).  ``metric``: original-space metric (any name of
+    ``pairwise_distance``); the embedded-space neighbours use Euclidean distance.  ``batch_size``: rows of
+    the original-space distance matrix alive at a time (0: about 1 GiB).  Returns a float."""
+    import ctypes
+    x_cai, e_cai = cai_wrapper(X), cai_wrapper(X_embedded)
+    x_cai.validate_shape_dtype(expected_dims=2, expected_dtype=np.float32)
+    e_cai.validate_shape_dtype(expected_dims=2, expected_dtype=np.float32)
+    if not (x_cai.c_contiguous and e_cai.c_contiguous):
+        raise ValueError("Inputs must be C contiguous")
+    n, m = x_cai.shape
+    if e_cai.shape[0] != n:
+        raise ValueError("Size mismatch between X and X_embedded")
+    d = e_cai.shape[1]
+    mt = int(resolve_metric(metric))
+    L = _lib.lib()
+    need = L.b2d_trustworthiness_score_workspace_bytes(n, m, d, int(n_neighbors), mt, int(batch_size))
+    if need == 2 ** 64 - 1:
+        raise _lib.LogicError("n_neighbors must be in [1, 63] and the metric one of pairwise_distance's")
+    ws = handle.workspace(need)
+    out = ctypes.c_double(0.0)
+    _lib.check(L.b2d_trustworthiness_score(handle.stream_ptr, ctypes.byref(out), x_cai.data, m, e_cai.data, d, n, m, d,
+                                           int(n_neighbors), mt, int(batch_size), ws.data_ptr(), ws.numel()))
+    return float(out.value)

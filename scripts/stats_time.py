@@ -10,3 +10,9 @@ for metric in ("sqeuclidean", "euclidean", "sqeuclidean_unexpanded", "cosine"):
     silhouette_score(x, lab, nl, metric=metric, handle=h); torch.cuda.synchronize()
     t = time.perf_counter(); v = silhouette_score(x, lab, nl, metric=metric, handle=h); torch.cuda.synchronize()
     print(f"silhouette {n}x{k}, {nl} labels, {metric}: {(time.perf_counter()-t)*1e3:.1f} ms  score {v:.4f}")
+from raft_b200.stats import trustworthiness_score
+emb = (x @ torch.randn(k, 2, device="cuda")).contiguous()
+for nn_ in (5, 15):
+    trustworthiness_score(x, emb, n_neighbors=nn_, handle=h); torch.cuda.synchronize()
+    t = time.perf_counter(); v = trustworthiness_score(x, emb, n_neighbors=nn_, handle=h); torch.cuda.synchronize()
+    print(f"trustworthiness {n}x{k} -> 2-d, n_neighbors {nn_}: {(time.perf_counter()-t)*1e3:.1f} ms  score {v:.4f}")

@@ -7,6 +7,7 @@
 #include <raft/distance/fused_l2_nn.cuh>
 #include <raft/neighbors/brute_force.cuh>
 #include <raft/stats/silhouette_score.cuh>
+#include <raft/stats/trustworthiness_score.cuh>
 
 int main()
 {
@@ -112,6 +113,12 @@ int main()
       }
       if (std::fabs(sc - tot / m) > 2e-4) { std::printf("silhouette %f vs %f\n", sc, tot / m); ++bad; }
       cudaFree(dl);
+    }
+    // raft::stats::trustworthiness_score: an embedding that IS the data scores exactly 1
+    {
+      const double tw = raft::stats::trustworthiness_score<float, raft::distance::DistanceType::L2SqrtUnexpanded>(
+        handle, x, x, m, k, k, 5, 128);
+      if (tw != 1.0) { std::printf("trustworthiness %f\n", tw); ++bad; }
     }
     // error convention: unsupported metric -> raft::logic_error
     bool threw = false;

@@ -148,3 +148,15 @@ def test_silhouette_oracle_pinned_to_sklearn():
         assert abs(got - skm.silhouette_score(x, labels, metric=sk)) < 1e-9
         assert np.allclose(per, skm.silhouette_samples(x, labels, metric=sk), atol=1e-9)
         assert per[0] == 0.0
+
+
+def test_trustworthiness_oracle_pinned_to_sklearn():
+    skm = pytest.importorskip("sklearn.manifold")
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((180, 10))
+    w = rng.standard_normal((10, 2))
+    good, bad = x @ w + 0.05 * rng.standard_normal((180, 2)), rng.standard_normal((180, 2))
+    for emb in (good, bad, x[:, :3]):
+        for k in (3, 7):
+            assert abs(oracle.trustworthiness_score(x, emb, k) - skm.trustworthiness(x, emb, n_neighbors=k)) < 1e-12
+    assert oracle.trustworthiness_score(x, x, 5) == 1.0

@@ -6,7 +6,7 @@ import torch
 
 import oracle
 from raft_b200 import LogicError
-from raft_b200.stats import silhouette_score
+from raft_b200.stats import silhouette_score, trustworthiness_score
 
 pytestmark = pytest.mark.gpu
 
@@ -61,3 +61,31 @@ def test_silhouette_argument_errors():
         silhouette_score(x, lab[:10], 8)
     from pylibraft.stats import silhouette_score as s2
     assert s2 is silhouette_score
+
+
+@pytest.mark.parametrize("shape", [(1200, 20, 2, 5), (700, 64, 8, 12), (300, 7, 3, 63)])
+@pytest.mark.parametrize("quality", ["projection", "random"])
+def test_trustworthiness_vs_oracle(shape, quality):
+    n, m, d, k = shape
+    rng = np.random.default_rng(n + k)
+    x = rng.standard_normal((n, m)).astype(np.float32)
+    if quality == "projection":
+        e = (x @ rng.standard_normal((m, d)).astype(np.float32)).astype(np.float32)
+    else:
+        e = rng.standard_normal((n, d)).astype(np.float32)
+    ref = oracle.trustworthiness_score(x, e, k)
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda()
+    got = trustworthiness_score(xt, et, n_neighbors=k)
+    assert abs(got - ref) < 1e-4, (got, ref)
+    assert abs(trustworthiness_score(xt, et, n_neighbors=k, metric="sqeuclidean_unexpanded", batch_size=256) - ref) < 1e-4
+    assert trustworthiness_score(xt, xt, n_neighbors=k) == 1.0
+
+
+def test_trustworthiness_argument_errors():
+    x = torch.randn(50, 6, device="cuda")
+    with pytest.raises(LogicError):
+        trustworthiness_score(x, x[:, :2].contiguous(), n_neighbors=64)
+    with pytest.raises(LogicError):
+        trustworthiness_score(x, x[:, :2].contiguous(), n_neighbors=40)      # >= n / 2
+    with pytest.raises(ValueError):
+        trustworthiness_score(x, x[:40, :2].contiguous())
