@@ -162,6 +162,13 @@ int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, 
                               int n_neighbors, int metric, int64_t batch_rows, void* workspace,
                               size_t workspace_bytes);
 
+/* Measurement aid (bench.py's roofline): between b2d_profile_begin(capacity) and b2d_profile_end every
+ * b2d_pairwise_distance call on the tensor path records a CUDA-event pair on ITS stream around its main
+ * kernel launch(es) (operand preparation excluded).  Nothing synchronises until b2d_profile_end, which
+ * waits for the recorded events and returns the durations in call order (milliseconds). */
+int b2d_profile_begin(int capacity);
+int b2d_profile_end(float* ms, int max_count, int* count);
+
 /* out[r] = norm of row r of x:[rows,k] (L2Norm = sum of squares; do_sqrt applies sqrt_op as
  * fin_op, cpp/include/raft/linalg/norm.cuh:118-147). */
 int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k,

@@ -14,7 +14,7 @@ SYMBOLS = [
     "b2d_fused_l2_nn_workspace_bytes", "b2d_fused_l2_nn", "b2d_fused_distance_nn", "b2d_fused_l2_nn_keys",
     "b2d_fused_l2_nn_finalize", "b2d_row_norm", "b2d_knn_l2_workspace_bytes", "b2d_knn_l2",
     "b2d_silhouette_score_workspace_bytes", "b2d_silhouette_score",
-    "b2d_trustworthiness_score_workspace_bytes", "b2d_trustworthiness_score",
+    "b2d_trustworthiness_score_workspace_bytes", "b2d_trustworthiness_score", "b2d_profile_begin", "b2d_profile_end",
 ]
 
 B2D_OK, B2D_ERR_INVALID_ARG, B2D_ERR_CUDA, B2D_ERR_UNSUPPORTED, B2D_ERR_WORKSPACE = range(5)
@@ -72,6 +72,10 @@ def lib() -> ctypes.CDLL:
     L.b2d_trustworthiness_score_workspace_bytes.argtypes = [i64, i64, i64, ci, ci, i64]
     L.b2d_trustworthiness_score.restype = ci
     L.b2d_trustworthiness_score.argtypes = [vp, vp, vp, i64, vp, i64, i64, i64, i64, ci, ci, i64, vp, sz]
+    L.b2d_profile_begin.restype = ci
+    L.b2d_profile_begin.argtypes = [ci]
+    L.b2d_profile_end.restype = ci
+    L.b2d_profile_end.argtypes = [vp, ci, vp]
     L.b2d_row_norm.restype = ci
     L.b2d_row_norm.argtypes = [vp, vp, vp, i64, i64, i64, ci, ci]
     _lib = L

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/raft_b200.h"
 #include "expanded_tc.cuh"
@@ -83,6 +84,36 @@ static int device_sms(int* sms, int* cc_major)
   B2D_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
   return B2D_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Optional timing of the dominant kernel (bench.py's roofline): CUDA events on the call's stream around
+// the main kernel of every b2d_pairwise_distance call between b2d_profile_begin and b2d_profile_end.
+// Nothing is synchronised until b2d_profile_end, so the timed region of the caller is not perturbed.
+namespace {
+struct ProfileRing {
+  std::vector<cudaEvent_t> ev;  // pairs
+  int used = 0;
+  bool on  = false;
+} g_prof;
+std::mutex g_prof_mu;
+
+struct ProfileScope {
+  cudaStream_t s;
+  int slot = -1;
+  explicit ProfileScope(cudaStream_t st) : s(st)
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof.on && 2 * (g_prof.used + 1) <= static_cast<int>(g_prof.ev.size())) {
+      slot = g_prof.used++;
+      cudaEventRecord(g_prof.ev[2 * slot], s);
+    }
+  }
+  ~ProfileScope()
+  {
+    if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], s);
+  }
+};
+}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // workspace layout of the tensor-core path
@@ -376,6 +407,35 @@ using namespace b2d;
 
 extern "C" {
 
+int b2d_profile_begin(int capacity)
+{
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (capacity < 1 || capacity > 4096) return fail(B2D_ERR_INVALID_ARG, "capacity must be in [1, 4096]");
+  while (static_cast<int>(g_prof.ev.size()) < 2 * capacity) {
+    cudaEvent_t e;
+    B2D_CUDA(cudaEventCreate(&e));
+    g_prof.ev.push_back(e);
+  }
+  g_prof.used = 0;
+  g_prof.on   = true;
+  return B2D_OK;
+}
+
+int b2d_profile_end(float* ms, int max_count, int* count)
+{
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.on = false;
+  if (!ms || !count || max_count < 0) return fail(B2D_ERR_INVALID_ARG, "null ms / count");
+  const int c = std::min(g_prof.used, max_count);
+  for (int i = 0; i < c; ++i) {
+    B2D_CUDA(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+    B2D_CUDA(cudaEventElapsedTime(&ms[i], g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+  }
+  *count = c;
+  return B2D_OK;
+}
+
+
 int b2d_version(void) { return 100; }
 const char* b2d_last_error(void) { return g_err.c_str(); }
 
@@ -445,6 +505,7 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     // add -- bounds the truncation bias of long MMA chains (numerics)
     const int nkb_total = static_cast<int>((k + 31) / 32);
     constexpr int kChunk = 8;
+    ProfileScope prof(s);  // the main kernel(s) only: the operand preparation above is outside
     if (nkb_total > 10) {
       for (int kb0 = 0; kb0 < nkb_total; kb0 += kChunk) {
         const int nk = nkb_total - kb0 < kChunk ? nkb_total - kb0 : kChunk;
