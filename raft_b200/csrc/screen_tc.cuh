@@ -182,16 +182,24 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int ch  = static_cast<int>(item / p.tiles_sel);
       const int mt0 = ch * p.chunk;
       const int mt1 = min(mt0 + p.chunk, p.tiles_m);
-      int mt        = mt0 + static_cast<int>((parity ^ t_it) & 1u);
-      if (mt >= mt1) {  // no tile of this item is ours: still release our half of the y-block barrier
+      // Both issuers wait for the y block and walk EVERY tile of the item, polling the x-stage barrier
+      // also for the tiles of the other issuer: an mbarrier parity wait is only sound for a waiter that is
+      // at most one phase behind, so no barrier may be skipped (a warp that skipped bfull of an item it
+      // owns no tile of -- items of a single tile, fewer than 129 query rows -- ran two phases ahead and
+      // issued MMAs on a y block that had not arrived).
+      ptx::mbar_wait(bfull, it_local & 1);
+      const int own0 = mt0 + static_cast<int>((parity ^ t_it) & 1u);   // our first tile of the item
+      if (own0 >= mt1) {  // none: our half of the y-block release (the bfull wait above closed the previous phase)
         if (ptx::elect_one()) ptx::mbar_arrive(bempty);
         __syncwarp();
-      } else {
-        ptx::mbar_wait(bfull, it_local & 1);
       }
-      for (; mt < mt1; mt += 2) {
+      for (int mt = mt0; mt < mt1; ++mt) {
         const uint32_t tt = t_it + static_cast<uint32_t>(mt - mt0);
         const uint32_t s = tt % n_stages, ph = (tt / n_stages) & 1;
+        if (((tt ^ parity) & 1u) != 0u) {  // the other issuer's tile: keep in step with its x stage only
+          ptx::mbar_wait(&afull[s], ph);
+          continue;
+        }
         ptx::mbar_wait(&tempty[parity], ((tt >> 1) & 1) ^ 1);
         ptx::mbar_wait(&afull[s], ph);
         ptx::tc_fence_after();

@@ -160,7 +160,8 @@ def test_row_norm_against_reference_spec():
 # ---- screened search (64 < k <= 128, n >= 16384): exact sub-sampled pass + coarse screen + exact
 # re-evaluation of the candidates (raft_b200/csrc/screen_tc.cuh)
 
-@pytest.mark.parametrize("shape", [(2000, 40000, 96), (1500, 20000, 128), (513, 33001, 70), (129, 16384, 65)])
+@pytest.mark.parametrize("shape", [(2000, 40000, 96), (1500, 20000, 128), (513, 33001, 70), (129, 16384, 65),
+                                   (96, 50000, 96), (1, 16384, 128), (128, 70000, 80)])
 @pytest.mark.parametrize("kind", ["blobs", "gauss"])
 def test_screened_nn_vs_oracle(shape, kind):
     m, n, k = shape
@@ -251,3 +252,24 @@ def test_sharded_head_exchange_path_matches_single():
         i2, v2 = fused_l2_nn_sharded(xt, yt, 0, sqrt=True, head_rows=head)
         # every finalist of the screened search is measured with the same direct fp32 arithmetic
         assert (i2 == i1).all() and torch.equal(v2, v1)
+
+
+def test_screened_nn_chunk_boundary():
+    """Database larger than one 2^20-row chunk: second chunk continues from the first one's keys, its
+    short remainder (< 16384 rows) takes the exact kernel; global indices on both sides of the boundary."""
+    rng = np.random.default_rng(31)
+    m, n, k = 96, (1 << 20) + 5000, 96
+    y = (rng.standard_normal((n, k)) * 2).astype(np.float32)
+    x = (rng.standard_normal((m, k)) * 2).astype(np.float32)
+    targets = [5, (1 << 20) - 1, 1 << 20, n - 1, 700000, (1 << 20) + 4999]
+    for i, t in enumerate(targets):
+        x[i] = y[t] + 1e-3
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=False, block=65536)
+    gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    assert gi[: len(targets)].tolist() == targets
+    tie_aware_index_check(gi, ri, x, y)
+    # the planted neighbours sit 1e-3 away from rows of norm ~20: the short remainder chunk is measured by
+    # the expanded form, whose cancellation floor is a few ulp of |x|^2 + |y|^2 (as in test_fuzz_gpu)
+    floor = 16 * 2.0 ** -24 * ((x.astype(np.float64) ** 2).sum(1) + (y[gi].astype(np.float64) ** 2).sum(1))
+    assert np.all(np.abs(gv - rv) <= 1e-4 * rv + floor)
