@@ -273,3 +273,17 @@ def test_screened_nn_chunk_boundary():
     # the expanded form, whose cancellation floor is a few ulp of |x|^2 + |y|^2 (as in test_fuzz_gpu)
     floor = 16 * 2.0 ** -24 * ((x.astype(np.float64) ** 2).sum(1) + (y[gi].astype(np.float64) ** 2).sum(1))
     assert np.all(np.abs(gv - rv) <= 1e-4 * rv + floor)
+
+
+def test_screened_nn_ragged_last_run_of_tiles():
+    """129 query tiles in runs of 32: the last run is a single tile, so single-tile and multi-tile work items
+    alternate on the same SM (the two MMA issuers must stay in step on every barrier)."""
+    rng = np.random.default_rng(77)
+    m, n, k = 16500, 40000, 96
+    x = (rng.standard_normal((m, k)) * 2).astype(np.float32)
+    y = (rng.standard_normal((n, k)) * 2).astype(np.float32)
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=False)
+    gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    tie_aware_index_check(gi, ri, x, y)
+    assert oracle.match_approx(gv, rv, 1e-4)[0]
