@@ -5,7 +5,8 @@ N = 1 : one step = raft_b200.distance.pairwise_distance L2Expanded 100000 x 1000
         (BASELINE.json configs[1]; operand prep + tcgen05 kernel), inputs resident in HBM.
         The line also carries the 1-GPU fusedL2NN number so the N>1 lines have their base.
 N > 1 : one step = fusedL2NN 1,000,000 queries x 8,000,000 db rows x 96 (configs[3]); the db is
-        row-sharded over the ranks, one packed min-loc all-reduce (NCCL, int64 MIN) per step.
+        row-sharded over the ranks, packed min-loc all-reduces (NCCL, int64 MIN; two per step: bounds
+        after a 32768-row head of every shard, result at the end).
         Strong scaling: total work fixed.
 --impl reference : the CPU restatement (oracle port: numpy expanded form on multithreaded BLAS,
         all host cores) on a bounded sample of the same workload.  The reference's own kernels for
@@ -404,7 +405,7 @@ def run_fused_nn_multi(args):
                 "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic make_blobs-like (5 centres U[-10,10]^k, sigma 1), generated on device",
                 "config": {"workload": "fusedL2NN 1000000 queries x 8000000 db x 96 fp32, db row-sharded",
-                           "parallelism": f"db_shard{world}", "exchange": "all_reduce(int64 MIN) of 1M packed (dist,idx) keys",
+                           "parallelism": f"db_shard{world}", "exchange": "2 x all_reduce(int64 MIN) of 1M packed (dist,idx) keys (bounds after a 32768-row head, result at the end)",
                            "l2": "db shard + queries exceed L2 for world<=8 (>=768 MB per rank)"},
                 "roofline": roof, "cpu_baseline": None,
                 "e2e": None, "gpu_launches": nn_launches(hi - lo, world) * args.steps, "clocks": cs.summary(),
