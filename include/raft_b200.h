@@ -107,7 +107,8 @@ int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, 
 
 /* raft::distance::fusedDistanceNN[MinReduce]: the same fused arg-min for
  * metric in {L2Expanded, L2SqrtExpanded, CosineExpanded, CorrelationExpanded}; out[i].value is the
- * distance in that metric.  xn / yn (optional) are squared L2 row norms and are used by the L2 metrics. */
+ * distance in that metric.  xn / yn (optional) are squared L2 row norms and are used by the L2 metrics.
+ * All four metrics take the screened search described at b2d_fused_l2_nn_keys when 64 < k <= 128. */
 int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float* x, int64_t ldx,
                           const float* y, int64_t ldy, const float* xn, const float* yn, int64_t m,
                           int64_t n, int64_t k, int init_out, void* workspace, size_t workspace_bytes);

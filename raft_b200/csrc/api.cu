@@ -294,7 +294,7 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
 // coarse screening pass of the screened fusedL2NN (screen_tc.cuh) over the y blocks with
 // sel_lo <= index % sel_s < sel_hi
 static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_t n, int64_t k, int sel_s, int sel_lo,
-                         int sel_hi, unsigned* overflow, const unsigned* run_flag)
+                         int sel_hi, unsigned* overflow, const unsigned* run_flag, int unit_norm)
 {
   int sms = 0, cc = 0;
   int rc  = device_sms(&sms, &cc);
@@ -319,7 +319,7 @@ static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_
   p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
   p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
   p.yt = w.yt; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
-  p.overflow = overflow; p.run_flag = run_flag;
+  p.overflow = overflow; p.run_flag = run_flag; p.unit_norm = unit_norm;
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb;
   rc = make_operand_map(&ma, w.xop, m, p.nkb, TC_BM, 0, 0, true);
@@ -565,7 +565,8 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
   const int nkb = static_cast<int>((k + 31) / 32);
   // (k <= 64: the exact kernel is already epilogue-bound, screening would not pay)
-  const bool screen = mode == PREP_L2 && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && allow_screen;
+  const bool screen = (mode == PREP_L2 || mode == PREP_COSINE) && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && allow_screen;
+  const int unit_norm = mode == PREP_COSINE ? 1 : 0;
   if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 
   // Screened search (screen_tc.cuh).  With S = 32 and r = index of a 256-row y block modulo S:
@@ -588,11 +589,11 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
                                                                          w.cand, flags, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr);
+  rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr, unit_norm);
   if (rc) return rc;
   nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 1);
   B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2);
+  rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2, unit_norm);
   if (rc) return rc;
   nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 2);
   B2D_CUDA(cudaGetLastError());
@@ -600,7 +601,7 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   rc = device_sms(&sms, &cc);
   if (rc) return rc;
   nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
-                                          ldy, static_cast<int>(k), idx_offset);
+                                          ldy, static_cast<int>(k), idx_offset, unit_norm, center);
   B2D_CUDA(cudaGetLastError());
   p.sel_lo = 1; p.sel_hi = 2; p.run_flag = flags + 4;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
@@ -641,7 +642,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   // The screened search (below) works through y in chunks of 2^20 rows: the candidate list is sized per
   // chunk, and every chunk starts from the bounds the earlier ones left in the keys.
   const int nkb_all    = static_cast<int>((k + 31) / 32);
-  const bool screen_ok = mode == PREP_L2 && nkb_all >= 3 && nkb_all <= TC_MAX_RES_KB && !screen_off;
+  const bool screen_ok = (mode == PREP_L2 || mode == PREP_COSINE) && nkb_all >= 3 && nkb_all <= TC_MAX_RES_KB && !screen_off;
   constexpr int64_t kChunkRows = 1 << 20;
   if (!screen_ok || n <= kChunkRows)
     return fused_nn_keys_chunk(s, keys, x, ldx, y, ldy, xn, yn, m, n, k, idx_offset, workspace, mode, center, screen_ok);

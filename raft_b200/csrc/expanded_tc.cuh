@@ -779,10 +779,13 @@ __global__ void nn_decide_kernel(unsigned* flags, unsigned m, float tau, int sta
   }
 }
 
-// one warp per candidate: d = sum (x_i - y_j)^2 in fp32 from the original inputs
+// one warp per candidate, straight from the original fp32 inputs:
+//   family 0  d = sum (x_i - y_j)^2
+//   family 1  d = 1 - <x', y'> / (|x'| |y'|), x' = x - mean(x) when centred (correlation), else x (cosine)
+// (k <= 128 on this path: a lane holds at most 4 elements of each row in registers)
 __global__ void __launch_bounds__(256) nn_exact_kernel(long long* keys, const int2* cand, const unsigned* cnt,
                                                        unsigned cap, const float* x, int64_t ldx, const float* y,
-                                                       int64_t ldy, int k, int64_t idx_offset)
+                                                       int64_t ldy, int k, int64_t idx_offset, int family, int center)
 {
   const int lane       = threadIdx.x & 31;
   const unsigned total = min(*cnt, cap);
@@ -792,16 +795,48 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(long long* keys, const in
     if (ij.x < 0) continue;
     const float* xr = x + static_cast<int64_t>(ij.x) * ldx;
     const float* yr = y + static_cast<int64_t>(ij.y) * ldy;
-    float acc       = 0.f;
-    for (int t = lane; t < k; t += 32) {
-      const float d = __ldg(xr + t) - __ldg(yr + t);
-      acc           = fmaf(d, d, acc);
-    }
+    float xv[4], yv[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int u = 0; u < 4; ++u) {
+      const int t = lane + 32 * u;
+      xv[u]       = t < k ? __ldg(xr + t) : 0.f;
+      yv[u]       = t < k ? __ldg(yr + t) : 0.f;
+    }
+    float res;
+    if (family == 0) {
+      float acc = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const float d = xv[u] - yv[u]; acc = fmaf(d, d, acc); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      res = acc;
+    } else {
+      float mx = 0.f, my = 0.f;
+      if (center) {
+        float sx = (xv[0] + xv[1]) + (xv[2] + xv[3]), sy = (yv[0] + yv[1]) + (yv[2] + yv[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+        mx = sx / static_cast<float>(k);
+        my = sy / static_cast<float>(k);
+      }
+      float dot = 0.f, nx = 0.f, ny = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool in = lane + 32 * u < k;
+        const float a = in ? xv[u] - mx : 0.f, b = in ? yv[u] - my : 0.f;
+        dot = fmaf(a, b, dot); nx = fmaf(a, a, nx); ny = fmaf(b, b, ny);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        nx += __shfl_xor_sync(0xffffffffu, nx, o);
+        ny += __shfl_xor_sync(0xffffffffu, ny, o);
+      }
+      res = 1.f - dot / sqrtf(nx * ny);
+    }
     if (lane == 0) {
       const long long gj  = static_cast<long long>(ij.y) + idx_offset;
-      const long long key = (static_cast<long long>(ordered_bits(acc)) << 32) | (gj & 0xFFFFFFFFll);
+      const long long key = (static_cast<long long>(ordered_bits(res)) << 32) | (gj & 0xFFFFFFFFll);
       atomicMin(&keys[ij.x], key);
     }
   }

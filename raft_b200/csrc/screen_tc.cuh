@@ -5,6 +5,7 @@
 // ONE tensor product per k-block (hi*hi only: a third of the exact kernel's MMA work, half of its
 // operand bytes) and computes, per pair, a rigorous LOWER bound of the fp32-grade distance
 //     L_ij = acc_ij * c + |y_j|^2 (1 - 2^-21) - 1.05 * 2^-9 |x_i| max_j' |y_j'|     (j' over the y block)
+// (cosine / correlation: rows are unit vectors after prep, d = 1 + acc * c, margin 1.05 * 2^-10)
 // (dropped cross terms: at most 2^-10 (1 + 2^-11) |x||y| in the dot product, i.e. 2^-9.. after the
 // factor 2; the remaining 5% of the margin and the 2^-21 |y|^2 cover the fp32 rounding of the
 // epilogue).  Only pairs with L_ij <= U_i can hold the minimum: they go to a candidate list that
@@ -77,6 +78,7 @@ struct ScreenParams {
   unsigned cand_cap;      // ... capacity ...
   unsigned* overflow;     // ... and overflow flag (then the exact pass re-runs)
   const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
+  int unit_norm;          // cosine family: rows are unit vectors, d = 1 + acc * c (c without the factor 2)
 };
 
 // 16 columns of this thread's row: lower bounds folded into four running minima (no branches: the
@@ -254,9 +256,14 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
         float tv = __int_as_float(0x7f800000), nyv = 0.f;  // +inf: never a candidate
         if (gj < p.n) {
-          tv  = __ldg(&p.yt[gj]);
-          nyv = sqrtf(tv) * (1.05f / 512.f);
-          tv  = tv - tv * (1.f / 2097152.f);
+          if (p.unit_norm) {  // |y_j| = 1 and no factor 2 in c: margin 1.05 * 2^-10, column term 0
+            tv  = 0.f;
+            nyv = 1.05f / 1024.f;
+          } else {
+            tv  = __ldg(&p.yt[gj]);
+            nyv = sqrtf(tv) * (1.05f / 512.f);
+            tv  = tv - tv * (1.f / 2097152.f);
+          }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nyv = fmaxf(nyv, __shfl_xor_sync(0xffffffffu, nyv, o));
@@ -267,7 +274,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       float ny_max = 0.f;
 #pragma unroll
       for (int i = 0; i < TC_BN / 32; ++i) ny_max = fmaxf(ny_max, col_ny[i]);
-      const float yn_max = (ny_max * (512.f / 1.05f)) * (ny_max * (512.f / 1.05f));  // max |y_j|^2 of the block
+      const float yn_max = p.unit_norm ? 1.f : (ny_max * (512.f / 1.05f)) * (ny_max * (512.f / 1.05f));  // max |y_j|^2 of the block
 
       const uint32_t t_item0 = t_it;
       for (; mt_own < mt1; mt_own += SC_SETS) {

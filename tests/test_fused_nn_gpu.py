@@ -287,3 +287,29 @@ def test_screened_nn_ragged_last_run_of_tiles():
     gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
     tie_aware_index_check(gi, ri, x, y)
     assert oracle.match_approx(gv, rv, 1e-4)[0]
+
+
+@pytest.mark.parametrize("metric", ["cosine", "correlation"])
+@pytest.mark.parametrize("shape", [(700, 30000, 96), (96, 20000, 128), (300, 17000, 70)])
+@pytest.mark.parametrize("kind", ["blobs", "gauss"])
+def test_screened_cosine_family_nn(metric, shape, kind):
+    """The screened search also serves the cosine family: rows are unit vectors after prep, the screen's
+    margin is 1.05 * 2^-10 and the candidates are re-measured as 1 - <x', y'> / (|x'||y'|) in fp32."""
+    m, n, k = shape
+    if kind == "blobs":
+        x, y = blobs(m, n, k, seed=21)
+    else:
+        rng = np.random.default_rng(5)
+        x = (rng.standard_normal((m, k)) + 0.3).astype(np.float32)
+        y = (rng.standard_normal((n, k)) + 0.3).astype(np.float32)
+    mt = oracle.DistanceType.CosineExpanded if metric == "cosine" else oracle.DistanceType.CorrelationExpanded
+    d = oracle.pairwise_distance(x, y, mt)
+    ri, rv = d.argmin(axis=1), d.min(axis=1)
+    gi, gv = fused_distance_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), metric=metric)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    bad = np.nonzero(gi != ri)[0]
+    assert len(bad) <= max(2, m // 500)
+    for i in bad:   # near-ties only
+        assert abs(d[i, gi[i]] - rv[i]) <= 2e-5 * max(rv[i], 1e-3)
+    # 1 - cos of near-parallel vectors: absolute floor of a few fp32 ulp of 1
+    assert np.all(np.abs(gv - rv) <= 1e-4 * np.abs(rv) + 4e-7)
