@@ -33,3 +33,16 @@ def test_shim_runs_on_gpu():
         compile_shim()
     res = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0 and "PASS" in res.stdout, res.stdout + res.stderr
+
+
+def test_block_selection_helpers_partition_the_blocks():
+    """sel_to_blk / sel_count (shared by the kernels and the launch code) on the host: the exact sample
+    pass, the trial screen and the main screen visit every y block exactly once, in ascending order."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = os.path.join(ROOT, "tests", "cpp", "host_logic_test")
+    cmd = [nvcc, "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+           os.path.join(ROOT, "tests", "cpp", "host_logic_test.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0 and "PASS" in res.stdout, res.stdout + res.stderr
