@@ -23,16 +23,17 @@
 // (1M x 1M x 96, cycles per tile): the first version re-used the exact kernel's roles and took 2300
 // -- the single MMA warp spent 740 issuing (tcgen05.mma issue blocks while the pipe's queue is full),
 // 810 + 690 in barrier polls and bookkeeping while the pipe idled, and the epilogue exposed one TMEM
-// load latency per fragment.  This kernel: ~1600 with everything on; isolation runs: operands + MMAs
-// alone 1010, epilogue alone 1100, synchronisation skeleton alone 620 -- the two halves still
-// contend (TMEM ports, issue slots) instead of overlapping fully.
+// load latency per fragment.  This kernel: ~1350 (ncu: tensor pipe 56 % active); isolation runs:
+// operands + MMAs alone 1010, epilogue alone 1100, synchronisation skeleton alone 620 -- the two halves
+// still contend (TMEM ports, issue slots) instead of overlapping fully.
 //   operands   hi halves only: TMA boxes of 32 fp16 (64 B, SWIZZLE_64B) out of the packed
 //              [hi32|lo32] k-blocks; a stage is one whole x tile (nkb x 8 KB), 5-6 stages deep,
 //              one mbarrier round trip per TILE; the y block (nkb x 16 KB) is resident per item
 //   MMA        two issuer warps, one per TMEM accumulator stage (even / odd tiles): while one is
 //              blocked in issue the other has finished its polls, so the pipe stays fed.  All waits
 //              first, then one elected region queues every MMA of the tile and the commits
-//              (x stage free, accumulator full)
+//              (x stage free, accumulator full).  Both issuers poll EVERY barrier in order, also for
+//              tiles they do not own: a parity wait is only sound at most one phase behind
 //   epilogue   16 warps on every tile (32 rows x 64 columns each), thread == row
 //              (tcgen05.ld.32x32b, the fastest TMEM read shape: 403 vs 571 cycles per tile for
 //              16x256b, scripts/probes/tmem_probe.cu), software-pipelined over two 16-column register
