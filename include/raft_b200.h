@@ -136,6 +136,11 @@ int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys,
  * out_dist the squared (do_sqrt != 0: Euclidean) distances.  The m x n matrix is never written.
  * n_neighbors <= 64, k <= 320.  The call synchronises the stream once per database pass. */
 size_t b2d_knn_l2_workspace_bytes(int64_t m, int64_t n, int64_t k, int64_t n_neighbors);
+/* the same for metric in {L2Expanded, L2Unexpanded, L2SqrtExpanded, L2SqrtUnexpanded, CosineExpanded,
+ * CorrelationExpanded} (workspace: b2d_knn_l2_workspace_bytes) */
+int b2d_knn(void* stream, int64_t* out_idx, float* out_dist, int metric, const float* x, int64_t ldx, const float* y,
+            int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, void* workspace,
+            size_t workspace_bytes);
 int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, int64_t ldx, const float* y,
                int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, int do_sqrt,
                void* workspace, size_t workspace_bytes);

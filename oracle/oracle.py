@@ -12,7 +12,7 @@ import numpy as np
 __all__ = [
     "DistanceType", "pairwise_distance", "fused_l2_nn", "row_norm_sq", "argmin_op",
     "row_argmin", "compare_approx", "match_approx", "make_blobs", "EXPANDED", "UNEXPANDED",
-    "pack_minloc", "unpack_minloc", "knn_l2", "silhouette_score", "trustworthiness_score",
+    "pack_minloc", "unpack_minloc", "knn_l2", "knn", "silhouette_score", "trustworthiness_score",
 ]
 
 
@@ -181,6 +181,18 @@ def fused_l2_nn(x, y, sqrt: bool = False, block: int = 4096):
     if sqrt:
         best_v = np.sqrt(best_v)
     return best_i.astype(np.int32), best_v
+
+
+def knn(x, y, n_neighbors: int, metric, block: int = 4096):
+    """k nearest rows of y under any metric of pairwise_distance, ascending by (distance, index) -- the
+    composition pairwise_distance + select_k(select_min, sorted) (see knn_l2)."""
+    x64 = np.ascontiguousarray(x, dtype=np.float64)
+    y64 = np.ascontiguousarray(y, dtype=np.float64)
+    m, n = x64.shape[0], y64.shape[0]
+    kk = int(n_neighbors)
+    d = np.concatenate([pairwise_distance(x64, y64[j0:j0 + block], metric) for j0 in range(0, n, block)], axis=1)
+    order = np.lexsort((np.broadcast_to(np.arange(n), d.shape), d), axis=1)[:, :kk]
+    return order.astype(np.int64), np.take_along_axis(d, order, axis=1)
 
 
 def knn_l2(x, y, n_neighbors: int, sqrt: bool = False, block: int = 4096):

@@ -12,7 +12,7 @@ _lib = None
 SYMBOLS = [
     "b2d_version", "b2d_last_error", "b2d_pairwise_workspace_bytes", "b2d_pairwise_distance",
     "b2d_fused_l2_nn_workspace_bytes", "b2d_fused_l2_nn", "b2d_fused_distance_nn", "b2d_fused_l2_nn_keys",
-    "b2d_fused_l2_nn_finalize", "b2d_row_norm", "b2d_knn_l2_workspace_bytes", "b2d_knn_l2",
+    "b2d_fused_l2_nn_finalize", "b2d_row_norm", "b2d_knn_l2_workspace_bytes", "b2d_knn_l2", "b2d_knn",
     "b2d_silhouette_score_workspace_bytes", "b2d_silhouette_score",
     "b2d_trustworthiness_score_workspace_bytes", "b2d_trustworthiness_score", "b2d_profile_begin", "b2d_profile_end",
 ]
@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
     L.b2d_fused_l2_nn_finalize.argtypes = [vp, vp, vp, i64, ci, vp, sz]
     L.b2d_knn_l2_workspace_bytes.restype = sz
     L.b2d_knn_l2_workspace_bytes.argtypes = [i64, i64, i64, i64]
+    L.b2d_knn.restype = ci
+    L.b2d_knn.argtypes = [vp, vp, vp, ci, vp, i64, vp, i64, i64, i64, i64, i64, vp, sz]
     L.b2d_knn_l2.restype = ci
     L.b2d_knn_l2.argtypes = [vp, vp, vp, vp, i64, vp, i64, i64, i64, i64, i64, ci, vp, sz]
     L.b2d_silhouette_score_workspace_bytes.restype = sz

@@ -789,7 +789,20 @@ int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, 
                int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, int do_sqrt, void* workspace,
                size_t workspace_bytes)
 {
+  return b2d_knn(stream, out_idx, out_dist, do_sqrt ? B2D_L2SqrtExpanded : B2D_L2Expanded, x, ldx, y, ldy, m, n, k,
+                 n_neighbors, workspace, workspace_bytes);
+}
+
+int b2d_knn(void* stream, int64_t* out_idx, float* out_dist, int metric, const float* x, int64_t ldx, const float* y,
+            int64_t ldy, int64_t m, int64_t n, int64_t k, int64_t n_neighbors, void* workspace, size_t workspace_bytes)
+{
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int mode = PREP_L2, center = 0, do_sqrt = 0;
+  if (metric == B2D_L2Expanded || metric == B2D_L2Unexpanded) {}
+  else if (metric == B2D_L2SqrtExpanded || metric == B2D_L2SqrtUnexpanded) do_sqrt = 1;
+  else if (metric == B2D_CosineExpanded) mode = PREP_COSINE;
+  else if (metric == B2D_CorrelationExpanded) { mode = PREP_COSINE; center = 1; }
+  else return fail(B2D_ERR_UNSUPPORTED, "kNN supports the L2 metrics, CosineExpanded and CorrelationExpanded");
   if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
   if (n_neighbors < 1 || n_neighbors > n) return fail(B2D_ERR_INVALID_ARG, "n_neighbors must be in [1, n]");
   if (n_neighbors > KNN_MAX_K) return fail(B2D_ERR_UNSUPPORTED, "n_neighbors > 64 is not supported");
@@ -813,7 +826,7 @@ int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, 
   c.thr      = reinterpret_cast<float*>(c.w.aux);          // [m] floats ...
   c.cnt      = reinterpret_cast<unsigned*>(c.w.aux) + m;   // ... and [m] counters share the aux block (8 B per row)
   c.overflow = c.w.cand_cnt;
-  int rc = launch_prep<float>(s, c.w, x, ldx, 1, m, y, ldy, 1, n, k, nullptr, nullptr, PREP_L2, 0);
+  int rc = launch_prep<float>(s, c.w, x, ldx, 1, m, y, ldy, 1, n, k, nullptr, nullptr, mode, center);
   if (rc) return rc;
   const int64_t total = m * n_neighbors;
   knn_init_kernel<<<static_cast<unsigned>((std::max<int64_t>(total, m) + 255) / 256), 256, 0, s>>>(c.topk, c.thr, c.cnt, c.overflow, m, c.kk);

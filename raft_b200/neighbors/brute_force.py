@@ -1,6 +1,6 @@
 """brute_force.knn -- mirror of ``pylibraft.neighbors.brute_force.knn`` (removed upstream together with
 the distance package, CHANGELOG.md:59-60): exact k nearest neighbours for the L2
-metrics, fused -- the m x n distance matrix is never materialised (raft_b200/csrc/expanded_tc.cuh,
+metrics and the cosine family, fused -- the m x n distance matrix is never materialised (raft_b200/csrc/expanded_tc.cuh,
 EPI_TOPK)."""
 from __future__ import annotations
 
@@ -9,8 +9,9 @@ import torch
 
 from .. import _lib
 from ..common import auto_sync_handle, cai_wrapper
+from ..distance.distance_type import resolve_metric
 
-_L2_METRICS = {"sqeuclidean": 0, "l2": 0, "euclidean": 1}
+_METRICS = ("sqeuclidean", "l2", "euclidean", "cosine", "correlation")
 
 
 @auto_sync_handle
@@ -21,9 +22,9 @@ def knn(dataset, queries, k=None, indices=None, distances=None, metric="sqeuclid
 
     dataset [n, d] and queries [m, d]: any C-contiguous float32 ``__cuda_array_interface__`` objects.
     ``indices`` / ``distances``: optional preallocated outputs (k is then read from their shape).
-    metric: "sqeuclidean" / "l2" (squared) or "euclidean"."""
-    if metric not in _L2_METRICS:
-        raise ValueError("metric %s is not supported by the fused kNN (L2 metrics only)" % metric)
+    metric: "sqeuclidean" (squared), "euclidean" / "l2", "cosine" or "correlation" (pylibraft's names)."""
+    if metric not in _METRICS:
+        raise ValueError("metric %s is not supported by the fused kNN (L2 metrics, cosine, correlation)" % metric)
     d_cai, q_cai = cai_wrapper(dataset), cai_wrapper(queries)
     d_cai.validate_shape_dtype(expected_dims=2, expected_dtype=np.float32)
     q_cai.validate_shape_dtype(expected_dims=2, expected_dtype=np.float32)
@@ -49,8 +50,8 @@ def knn(dataset, queries, k=None, indices=None, distances=None, metric="sqeuclid
     if need == 2 ** 64 - 1:
         raise _lib.LogicError("k must be between 1 and 64")
     ws = handle.workspace(need)
-    _lib.check(L.b2d_knn_l2(handle.stream_ptr, idx.data_ptr(), dist.data_ptr(), q_cai.data, dim, d_cai.data, dim,
-                            m, n, dim, k, _L2_METRICS[metric], ws.data_ptr(), ws.numel()))
+    _lib.check(L.b2d_knn(handle.stream_ptr, idx.data_ptr(), dist.data_ptr(), int(resolve_metric(metric)), q_cai.data, dim,
+                         d_cai.data, dim, m, n, dim, k, ws.data_ptr(), ws.numel()))
     if global_id_offset:
         with torch.cuda.stream(handle.torch_stream):
             idx += int(global_id_offset)

@@ -95,10 +95,28 @@ def test_knn_arguments_and_outputs():
     with pytest.raises(ValueError):
         brute_force.knn(y, x)                       # k unknown
     with pytest.raises(ValueError):
-        brute_force.knn(y, x, k=3, metric="cosine")
+        brute_force.knn(y, x, k=3, metric="cityblock")
     with pytest.raises(LogicError):
         brute_force.knn(y, x, k=65)                 # above the supported k
     with pytest.raises(LogicError):
         brute_force.knn(y[:3], x, k=4)              # k > n
     from pylibraft.neighbors import brute_force as bf2
     assert bf2.knn is brute_force.knn
+
+
+@pytest.mark.parametrize("metric", ["cosine", "correlation"])
+@pytest.mark.parametrize("shape", [(400, 6000, 48, 12), (129, 20000, 96, 40)])
+def test_knn_cosine_family(metric, shape):
+    m, n, k, kk = shape
+    rng = np.random.default_rng(m + kk)
+    x = (rng.standard_normal((m, k)) + 0.4).astype(np.float32)
+    y = (rng.standard_normal((n, k)) + 0.4).astype(np.float32)
+    mt = oracle.DistanceType.CosineExpanded if metric == "cosine" else oracle.DistanceType.CorrelationExpanded
+    ri, rv = oracle.knn(x, y, kk, mt)
+    gd, gi = brute_force.knn(torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda(), k=kk, metric=metric)
+    gd, gi = gd.cpu().numpy(), gi.cpu().numpy()
+    assert np.all(np.diff(gd, axis=1) >= 0) and all(len(set(r.tolist())) == kk for r in gi)
+    assert np.all(np.abs(gd - rv) <= 1e-4 * np.abs(rv) + 4e-7)
+    assert (gi != ri).mean() < 0.01
+    true_d = np.take_along_axis(oracle.pairwise_distance(x, y, mt), gi, axis=1)
+    assert np.all(np.abs(gd - true_d) <= 1e-4 * np.abs(true_d) + 4e-7)
