@@ -11,6 +11,8 @@ r = lambda *s: torch.randn(*s, device="cuda", generator=g)
 x, y = r(300, 96), r(20000, 96)
 i, v = fused_l2_nn(x, y, sqrt=False)                       # screened search: sample / trial / main / exact
 print("nn screened", int(i.sum()), float(v.sum()))
+i, v = fused_l2_nn(r(96, 128), r(40000, 128), sqrt=False)  # single-tile work items, many per SM
+i, v = fused_distance_nn(r(200, 96) + 0.5, r(20000, 96) + 0.5, metric="correlation")   # screened, cosine family
 i, v = fused_l2_nn(r(300, 40), r(700, 40))                 # exact kernel only
 i, v = fused_distance_nn(r(130, 200), r(300, 200), metric="cosine")   # streaming (k > 128) arg-min
 d = pairwise_distance(r(257, 100), r(515, 100), metric="sqeuclidean")  # TMA-store epilogue? n % 4 != 0 -> direct
@@ -19,8 +21,12 @@ d = pairwise_distance(r(100, 700), r(90, 700), metric="sqeuclidean")   # K-chunk
 d = pairwise_distance(r(130, 33), r(70, 33), metric="cityblock")       # SIMT loader
 d = pairwise_distance(r(128, 64), r(256, 64), metric="chebyshev")      # TMA-fed FP32 kernel
 dd, ii = brute_force.knn(r(3000, 32), r(200, 32), k=8)
+dd, ii = brute_force.knn(r(2000, 70) + 0.3, r(100, 70) + 0.3, k=5, metric="cosine")
 print("knn", int(ii.sum()))
 lab = torch.randint(0, 4, (500,), device="cuda", dtype=torch.int32, generator=g)
 print("silhouette", silhouette_score(r(500, 16), lab, 4))
+from raft_b200.stats import trustworthiness_score
+xx = r(600, 20)
+print("trustworthiness", trustworthiness_score(xx, xx[:, :3].contiguous(), n_neighbors=7))
 torch.cuda.synchronize()
 print("done")
