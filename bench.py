@@ -365,8 +365,12 @@ def run_fused_nn_multi(args):
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # NCCL writes its version banner (and any NCCL_DEBUG output) to the C-level stdout: park fd 1 on stderr for
+    # the whole run and write the single JSON line to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_src = measured_peaks()
     m, n, k = FUSED_NN["m"], FUSED_NN["n"], FUSED_NN["k"]
@@ -437,7 +441,8 @@ def run_fused_nn_multi(args):
                        "h2d_bytes_per_step": 4 * k * (m + (hi - lo)), "d2h_bytes_per_step": 8 * m,
                        "ms_per_step": float(t.item()) * 1e3, "steps": e2e_steps,
                        "path": "pinned H2D of queries + this rank's db shard, fused_l2_nn_sharded, D2H of (idx,dist)"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
