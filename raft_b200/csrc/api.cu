@@ -671,7 +671,8 @@ int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys,
   if (m == 0) return B2D_OK;
   if (!out || !keys || !workspace) return fail(B2D_ERR_INVALID_ARG, "null out / keys / workspace");
   if (workspace_bytes < 1024 + static_cast<size_t>(m) * 4) return fail(B2D_ERR_WORKSPACE, "workspace too small");
-  TcWorkspace w = tc_layout(const_cast<void*>(workspace), m, 0, 0, true);
+  // (the keys hold the full distance, so nothing is read back from the workspace any more; the argument stays
+  // for ABI stability)
   minloc_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(
     reinterpret_cast<KvpIF*>(out), reinterpret_cast<const long long*>(keys), m, do_sqrt, 0);
   B2D_CUDA(cudaGetLastError());
