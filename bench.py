@@ -3,11 +3,15 @@
 
 N = 1 : one step = raft_b200.distance.pairwise_distance L2Expanded 100000 x 100000 x 128 fp32
         (BASELINE.json configs[1]; operand prep + tcgen05 kernel), inputs resident in HBM.
-        The line also carries the 1-GPU fusedL2NN number so the N>1 lines have their base.
+        After the timed region the result of the last step is CHECKED (fp64 re-evaluation of sampled pairs on
+        the device, oracle/device_check.py -> "parity"), the GPU baselines are timed on the same shapes in the
+        same process ("gpu_baselines": cuBLASLt-SGEMM composition of the reference's surviving primitives,
+        torch.cdist, a runtime probe for pylibraft / cuvs), and the other BASELINE configs are timed + checked.
 N > 1 : one step = fusedL2NN 1,000,000 queries x 8,000,000 db rows x 96 (configs[3]); the db is
-        row-sharded over the ranks, packed min-loc all-reduces (NCCL, int64 MIN; two per step: bounds
-        after a 32768-row head of every shard, result at the end).
-        Strong scaling: total work fixed.
+        row-sharded over the ranks, packed min-loc all-reduces (NCCL, int64 MIN).  Strong scaling: total work
+        fixed.  Rank 0 first runs the SAME job un-sharded on its own GPU (same session, same data), so every
+        line carries "scaling": {t1_ms, tN_ms, speedup, efficiency}; every rank checks the reduced result
+        against the exact fp64 arg-min over its own shard (combined across ranks) -> "parity".
 --impl reference : the CPU restatement (oracle port: numpy expanded form on multithreaded BLAS,
         all host cores) on a bounded sample of the same workload.  The reference's own kernels for
         this path are not in /root/reference, so there is nothing else to run.
@@ -40,10 +44,12 @@ def measured_peaks():
 
 def ncu_traffic(name):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]
-    except Exception:
-        return None
+    for f in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", f)))[name]
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -208,9 +214,94 @@ def time_steps(fn, steps, warmup, torch, sync_all=None):
     return total / steps, per
 
 
+def gpu_baselines_pairwise(x, y, out, m, n, k, ours_ms, torch, steps=5, warm=2):
+    """GPU baselines for configs[1] (L2Expanded m x n x k fp32), timed like the engine (CUDA events, output buffer
+    reused; every step streams 40+ GB through the 126 MB L2, so nothing is cached between steps)."""
+    import baseline
+    res = {}
+    dev = x.device
+    # (i) what the reference's surviving primitives compose to (baseline/gpu_composition.cu)
+    try:
+        L = baseline.lib()
+        baseline.check(L.bl_init())
+        xn = torch.empty(m, device=dev)
+        yn = torch.empty(n, device=dev)
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        fn = lambda: baseline.check(L.bl_pairwise_l2(st, out.data_ptr(), x.data_ptr(), y.data_ptr(), xn.data_ptr(),
+                                                     yn.data_ptr(), m, n, k, 0, ws.data_ptr(), ws.numel()))
+        ms, _ = time_steps(fn, steps, warm, torch)
+        from oracle import device_check as dc
+        par = dc.check_pairwise_sampled(out, x, y, 0, count=50_000, eps=1e-4)
+        res["cublaslt_sgemm_composition"] = {
+            "ms": ms, "pairs_per_s": m * n / (ms * 1e-3),
+            "what": "row norms + cublasLtMatmul fp32 (CUBLAS_COMPUTE_32F, no TF32) + one elementwise pass: the composition "
+                    "of raft::linalg::norm / gemm / map_offset (cublaslt_wrappers.hpp:35-38,268-313) -- 3 passes over m x n",
+            "parity_vs_fp64": par, "speedup_of_engine": ms / ours_ms}
+        del xn, yn, ws
+    except Exception as e:  # noqa: BLE001
+        res["cublaslt_sgemm_composition"] = {"unavailable": repr(e)[:200]}
+    # (ii) torch.cdist (cuBLAS SGEMM path, TF32 off = torch default) -- needs its own 40 GB result (+ temporaries)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        fn = lambda: torch.cdist(x, y, p=2.0, compute_mode="use_mm_for_euclid_dist")
+        ms, _ = time_steps(fn, 3, 1, torch)
+        res["torch_cdist"] = {"ms": ms, "pairs_per_s": m * n / (ms * 1e-3), "speedup_of_engine": ms / ours_ms,
+                              "what": "torch.cdist(p=2, use_mm_for_euclid_dist): euclidean (sqrt) distances, allocates its own output"}
+    except Exception as e:  # noqa: BLE001
+        res["torch_cdist"] = {"unavailable": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    # (iii) the reference's own GPU kernels, if some RAFT <= 25.12 / cuVS wheel is importable on this box
+    probe = {}
+    for mod in ("pylibraft.distance", "cuvs.distance"):
+        try:
+            __import__(mod)
+            probe[mod] = "importable (not timed: unexpected on this image)"
+        except Exception as e:  # noqa: BLE001
+            probe[mod] = "not importable: " + type(e).__name__
+    res["reference_gpu_kernels_probe"] = probe
+    return res
+
+
+def gpu_baseline_nn_sample(q, db, ours_pairs_per_s, torch, mq=65536, nd=1 << 20, chunk=131072):
+    """fusedL2NN by composition (SGEMM + elementwise + row arg-min per db chunk, baseline/gpu_composition.cu) on a
+    bounded sample of the 1M x 8M job: mq queries x nd db rows; the rate is per pair, the full job is 122x the sample."""
+    import baseline
+    try:
+        L = baseline.lib()
+        dev = q.device
+        k = q.shape[1]
+        xs, ys = q[:mq].contiguous(), db[:nd].contiguous()
+        tile = torch.empty((mq, chunk), dtype=torch.float32, device=dev)
+        xn, yn = torch.empty(mq, device=dev), torch.empty(chunk, device=dev)
+        bv, bi = torch.empty(mq, device=dev), torch.empty(mq, dtype=torch.int32, device=dev)
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        fn = lambda: baseline.check(L.bl_l2_nn(st, bv.data_ptr(), bi.data_ptr(), xs.data_ptr(), ys.data_ptr(), tile.data_ptr(),
+                                               xn.data_ptr(), yn.data_ptr(), mq, nd, k, chunk, ws.data_ptr(), ws.numel()))
+        ms, _ = time_steps(fn, 3, 1, torch)
+        rate = mq * nd / (ms * 1e-3)
+        return {"ms_sample": ms, "sample": f"{mq} queries x {nd} db rows x {k} (chunks of {chunk} db rows), extrapolated per pair",
+                "pairs_per_s": rate, "speedup_of_engine": ours_pairs_per_s / rate,
+                "what": "cublasLt SGEMM (CUBLAS_COMPUTE_32F) + elementwise pass + row arg-min pass per chunk, merged across chunks"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+
+
+def nn_parity_1gpu(idx, val, q, db, torch, sample=16384, seed=3):
+    from oracle import device_check as dc
+    g = torch.Generator(device=q.device).manual_seed(seed)
+    rows = torch.randperm(q.shape[0], device=q.device, generator=g)[:sample]
+    ref_val, ref_idx = dc.nn_exact_fp64(q[rows], db)
+    r = dc.check_nn(idx[rows], val[rows], ref_val, ref_idx, q[rows], lambda ix: db[ix])
+    r["what"] = f"{sample} sampled queries vs the exact fp64 arg-min over all {db.shape[0]} db rows"
+    return r
+
+
 def run_pairwise_1gpu(args):
     import numpy as np
     import torch
+    from oracle import device_check as dc
     from raft_b200.common import DeviceResources
     from raft_b200.distance import HostPairwise, fused_l2_nn, pairwise_distance
     dev = torch.device("cuda", 0)
@@ -235,6 +326,7 @@ def run_pairwise_1gpu(args):
         if state["n"] == args.warmup + 1:          # first timed step
             _lib.check(L.b2d_profile_begin(max(1, args.steps)))
         fn()
+    out.fill_(float("nan"))
     with ClockSampler(0) as cs:
         ms, per = time_steps(fn_counted, args.steps, args.warmup, torch)
     kbuf = (ctypes.c_float * max(1, args.steps))()
@@ -244,6 +336,10 @@ def run_pairwise_1gpu(args):
     k_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else ms
     clocks = cs.summary()
     pairs = m * n
+    # ---- parity of what was just timed: the result of the last timed step, re-evaluated in fp64 on the device
+    parity = dc.check_pairwise_sampled(out, x, y, 0, count=200_000, eps=1e-4)
+    parity["what"] = "L2Expanded 100000x100000x128: sampled pairs incl. tile corners / matrix edges vs fp64, CompareApprox(1e-4)"
+    parity["every_tile_written"] = bool(torch.isfinite(out[::127, ::251]).all().item())
     alg_bytes = 4 * (m * k + n * k) + 4 * m * n
     roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, copy read+write)",
@@ -254,27 +350,34 @@ def run_pairwise_1gpu(args):
                            "note": "the same bytes over the whole step, i.e. incl. the two operand-prep launches"},
             "traffic": ncu_traffic("pairwise_100k")}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    # ---- the other BASELINE.json configs, timed briefly in the same run (parity for them lives in tests/)
+    # ---- GPU baselines on the same shapes, same process, same timing method
+    gpu_bl = gpu_baselines_pairwise(x, y, out, m, n, k, ms, torch)
+    # ---- the other BASELINE.json configs, timed briefly in the same run AND checked (sampled fp64 re-evaluation)
     others = {}
 
     def t_ms(f, steps=3, warm=1):
         ms_, _ = time_steps(f, steps, warm, torch)
         return ms_
-    for metric in ("cosine", "correlation"):
+
+    def chk(o, xs, ys, metric, count=100_000, row_offset=0):
+        r = dc.check_pairwise_sampled(o, xs, ys, metric, count=count, eps=1e-4, row_offset=row_offset)
+        return {"checked": r["checked"], "n_bad": r["n_bad"], "max_rel_err": r["max_rel_err"]}
+    for metric, mt in (("cosine", 2), ("correlation", 10)):
         ms_o = t_ms(lambda: pairwise_distance(x, y, out=out, metric=metric, handle=h))
         others[f"{metric} 100000x100000x128 f32"] = {"ms": ms_o, "pairs_per_s": pairs / (ms_o * 1e-3),
-                                                     "hbm_gbs": alg_bytes / (ms_o * 1e-3) / 1e9}
+                                                     "hbm_gbs": alg_bytes / (ms_o * 1e-3) / 1e9, "parity": chk(out, x, y, mt)}
     m3, k3 = 50_000, 256
     c3 = centers_device(k3, torch, dev)
     x3 = blobs_device(m3, k3, 1234, c3, torch, dev)
     y3 = blobs_device(m3, k3, 4321, c3, torch, dev)
     out3 = out.view(-1)[: m3 * m3].view(m3, m3)
-    for metric, name in (("cityblock", "L1"), ("sqeuclidean_unexpanded", "L2Unexpanded"), ("chebyshev", "Linf")):
+    for metric, name, mt in (("cityblock", "L1", 3), ("sqeuclidean_unexpanded", "L2Unexpanded", 4), ("chebyshev", "Linf", 7)):
         ms_o = t_ms(lambda: pairwise_distance(x3, y3, out=out3, metric=metric, handle=h), steps=2)
         others[f"{name} 50000x50000x256 f32"] = {
             "ms": ms_o, "pairs_per_s": m3 * m3 / (ms_o * 1e-3),
             "hbm_gbs": (8.0 * m3 * k3 + 4.0 * m3 * m3) / (ms_o * 1e-3) / 1e9,
-            "fp32_lane_ops_per_s": 2.0 * m3 * m3 * k3 / (ms_o * 1e-3), "bound": "fp32 pipe (148 SMs x 128 lanes x clk)"}
+            "fp32_lane_ops_per_s": 2.0 * m3 * m3 * k3 / (ms_o * 1e-3), "bound": "fp32 pipe (148 SMs x 128 lanes x clk)",
+            "parity": chk(out3, x3, y3, mt)}
     del x3, y3
     # fused brute-force kNN: top-16 of every row of the 100000x100000x128 problem, matrix never written
     from raft_b200.neighbors import brute_force
@@ -292,7 +395,8 @@ def run_pairwise_1gpu(args):
             pairwise_distance(x5[r0:r0 + blk], y5, out=out5, metric="sqeuclidean", handle=h)
     ms_o = t_ms(fp16_pass, steps=2)
     others["L2Expanded 200000x200000x64 f16-in/f32-acc (4 row blocks, reused 40 GB buffer)"] = {
-        "ms": ms_o, "pairs_per_s": float(m5) * m5 / (ms_o * 1e-3), "hbm_gbs": 4.0 * m5 * m5 / (ms_o * 1e-3) / 1e9}
+        "ms": ms_o, "pairs_per_s": float(m5) * m5 / (ms_o * 1e-3), "hbm_gbs": 4.0 * m5 * m5 / (ms_o * 1e-3) / 1e9,
+        "parity": dict(chk(out5, x5, y5, 0, row_offset=m5 - blk), note="last row block, vs the fp16-rounded inputs")}
     del x5, y5, out5, out3
     del out
     torch.cuda.empty_cache()
@@ -315,13 +419,18 @@ def run_pairwise_1gpu(args):
     del hp
     torch.cuda.empty_cache()
 
-    # ---- 1-GPU fusedL2NN (base of the multi-GPU scaling lines)
+    # ---- 1-GPU fusedL2NN (configs[3] on one GPU): timed, checked, and the composition baseline beside it
     fm, fn_, fk = FUSED_NN["m"], FUSED_NN["n"], FUSED_NN["k"]
     c2 = centers_device(fk, torch, dev)
     q = blobs_device(fm, fk, 1234, c2, torch, dev)
-    db = blobs_device(fn_, fk, 4321, c2, torch, dev)
+    db = torch.cat([blobs_device(hi - lo, fk, 4321 + r, c2, torch, dev) for r, (lo, hi) in
+                    enumerate([(fn_ * r // 8, fn_ * (r + 1) // 8) for r in range(8)])])   # the 8-rank job's database
     nn_steps = max(1, min(args.steps, 2))
-    nn_ms, _ = time_steps(lambda: fused_l2_nn(q, db, sqrt=False, handle=h), nn_steps, 1, torch)
+    res = {}
+
+    def nn_step():
+        res["iv"] = fused_l2_nn(q, db, sqrt=False, handle=h)
+    nn_ms, _ = time_steps(nn_step, nn_steps, 1, torch)
     nn = {"workload": "fusedL2NN 1000000x8000000x96 fp32, 1 GPU", "value": fm * fn_ / (nn_ms * 1e-3),
           "unit": "pairs/s", "ms_per_step": nn_ms, "steps": nn_steps,
           "roofline": {"bound": "tensor", "achieved": 2.0 * fm * fn_ * fk / (nn_ms * 1e-3) / 1e12,
@@ -331,6 +440,8 @@ def run_pairwise_1gpu(args):
                                "1/32 of the blocks, 1-product screen on the rest, exact re-evaluation of the candidates) "
                                "executes ~1.06x"}}
     nn["roofline"]["frac"] = nn["roofline"]["achieved"] / nn["roofline"]["peak"]
+    nn["parity"] = nn_parity_1gpu(res["iv"][0], res["iv"][1], q, db, torch)
+    nn["gpu_baseline_composition"] = gpu_baseline_nn_sample(q, db, nn["value"], torch)
     del q, db
 
     cb, _, _ = cpu_baseline("pairwise", seconds_budget=10.0)
@@ -341,8 +452,9 @@ def run_pairwise_1gpu(args):
             "config": {"workload": "pairwise_distance L2Expanded 100000x100000x128 fp32 -> fp32 [m,n]",
                        "precision": "fp32-grade: 3-term fp16 hi/lo split, fp32 accumulate in TMEM",
                        "l2": "every step streams 40 GB of output through the 126 MB L2 (no reuse across steps)"},
-            "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 3 * args.steps,
-            "clocks": clocks, "fused_l2_nn": nn, "other_configs": others, "ms_per_step_all": [round(v, 4) for v in per]}
+            "roofline": roof, "parity": parity, "gpu_baselines": gpu_bl, "cpu_baseline": cb, "e2e": e2e,
+            "gpu_launches": 3 * args.steps, "clocks": clocks, "fused_l2_nn": nn, "other_configs": others,
+            "ms_per_step_all": [round(v, 4) for v in per]}
     print(json.dumps(line))
 
 
@@ -350,17 +462,18 @@ def nn_launches(shard_rows, world):
     """Kernels of this repo per sharded fusedL2NN call (api.cu fused_nn_keys): per b2d_fused_l2_nn_keys call and
     1M-row chunk: 2 prep + exact sample + seed + trial screen + decide + main screen + decide + candidate
     re-evaluation + 2 conditional exact passes = 11; + key init + finalize."""
-    from raft_b200.distance.fused_l2_nn import SHARD_HEAD_ROWS
-    head = SHARD_HEAD_ROWS if (world > 1 and shard_rows >= 4 * SHARD_HEAD_ROWS) else 0
+    from raft_b200.distance.fused_l2_nn import plan_exchanges
+    calls = plan_exchanges(shard_rows, world)   # (shard_rows: n_total // world)
     chunks = lambda n: max(1, -(-n // (1 << 20)))
-    return 11 * ((1 if head else 0) + chunks(shard_rows - head)) + 2
+    return 11 * sum(chunks(c) for c in calls) + 2
 
 
 def run_fused_nn_multi(args):
     import torch
     import torch.distributed as dist
+    from oracle import device_check as dc
     from raft_b200.common import DeviceResources
-    from raft_b200.distance import fused_l2_nn_sharded, shard_bounds
+    from raft_b200.distance import fused_l2_nn, fused_l2_nn_sharded, shard_bounds
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     dev = torch.device("cuda", local)
@@ -377,17 +490,44 @@ def run_fused_nn_multi(args):
     c = centers_device(k, torch, dev)
     q = blobs_device(m, k, 1234, c, torch, dev)                 # queries replicated (same seed on every rank)
     lo, hi = shard_bounds(n, world, rank)
-    db = blobs_device(hi - lo, k, 4321 + rank, c, torch, dev)   # this rank's row block of the database
-    h = DeviceResources()
-    keys = torch.empty(m, dtype=torch.int64, device=dev)
+    # the database is defined by its 8 row blocks (seed 4321 + block): a rank generates the blocks of its shard, so the
+    # 1-, 2-, 4- and 8-GPU runs (and rank 0's un-sharded base run below) all search the SAME 8M rows
+    blocks = [(n * r // 8, n * (r + 1) // 8) for r in range(8)]
 
-    def step():
-        fused_l2_nn_sharded(q, db, lo, sqrt=False, handle=h, keys=keys)
+    def db_rows(a, b):
+        parts = []
+        for r, (blo, bhi) in enumerate(blocks):
+            s0, s1 = max(a, blo), min(b, bhi)
+            if s0 < s1:
+                blk = blobs_device(bhi - blo, k, 4321 + r, c, torch, dev)
+                parts.append(blk[s0 - blo:s1 - blo])
+        return torch.cat(parts) if len(parts) > 1 else parts[0].contiguous()
+    h = DeviceResources()
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+
+    # ---- same-session 1-GPU base of the scaling record: rank 0 runs the whole job un-sharded (others wait)
+    t1_ms, base = None, None
+    if rank == 0:
+        full = db_rows(0, n)
+        r1 = {}
+
+        def base_step():
+            r1["iv"] = fused_l2_nn(q, full, sqrt=False, handle=h)
+        t1_ms, _ = time_steps(base_step, 2, 1, torch)
+        base = (r1["iv"][0].clone(), r1["iv"][1].clone())
+        del full, r1
+        torch.cuda.empty_cache()
+    sync_all()
+    db = db_rows(lo, hi)                                        # this rank's row block of the database
+    keys = torch.empty(m, dtype=torch.int64, device=dev)
+    last = {}
+
+    def step():
+        last["iv"] = fused_l2_nn_sharded(q, db, lo, sqrt=False, handle=h, keys=keys, n_total=n)
 
     with ClockSampler(local) as cs:
         ms, per = time_steps(step, args.steps, args.warmup, torch, sync_all=sync_all)
@@ -395,6 +535,45 @@ def run_fused_nn_multi(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # ---- parity on EVERY rank: the reduced result vs the exact fp64 arg-min (own shard, combined across ranks)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rows = torch.randperm(m, device=dev, generator=g)[:8192]
+    lv, la = dc.nn_exact_fp64(q[rows], db, idx_offset=lo)       # exact over this shard, GLOBAL indices
+    if world > 1:
+        allv = [torch.empty_like(lv) for _ in range(world)]
+        alla = [torch.empty_like(la) for _ in range(world)]
+        dist.all_gather(allv, lv)
+        dist.all_gather(alla, la)
+        V, A = torch.stack(allv), torch.stack(alla)
+        gv = V.min(dim=0).values
+        ga = torch.where(V == gv[None, :], A, torch.full_like(A, 2 ** 62)).min(dim=0).values   # ties -> smaller index
+    else:
+        gv, ga = lv, la
+    gi, gval = last["iv"][0][rows], last["iv"][1][rows]
+    # fp64 distance of the row the engine chose: computed by the rank that owns it, summed across ranks
+    own = (gi.long() >= lo) & (gi.long() < hi)
+    dsel = torch.zeros(rows.numel(), dtype=torch.float64, device=dev)
+    if int(own.sum()):
+        dsel[own] = ((q[rows[own]].double() - db[gi.long()[own] - lo].double()) ** 2).sum(1)
+    if world > 1:
+        dist.all_reduce(dsel)
+    same = gi.long() == ga
+    gap = (dsel - gv).abs() / gv.clamp_min(1e-300)
+    n_bad_val, max_rel = dc.compare_approx(gval, gv, 1e-4)
+    par = torch.tensor([float(same.float().mean()), float((same | (gap <= 1e-6)).float().mean()), float(n_bad_val), max_rel],
+                       dtype=torch.float64, device=dev)
+    pmin, pmax = par.clone(), par.clone()
+    if world > 1:
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+    parity = {"checked_per_rank": int(rows.numel()), "ranks": world,
+              "idx_strict_match": float(pmin[0]), "idx_tie_aware_match": float(pmin[1]), "val_n_bad": int(pmax[2]),
+              "val_max_rel_err": float(pmax[3]),
+              "what": "every rank: 8192 sampled queries, reduced (idx, dist) vs the exact fp64 arg-min over all shards "
+                      "(per-shard fp64 minima all_gathered); worst rank reported"}
+    if rank == 0 and base is not None:
+        parity["sharded_equals_unsharded"] = {"idx_equal_frac": float((base[0] == last["iv"][0]).float().mean()),
+                                              "val_equal_frac": float((base[1] == last["iv"][1]).float().mean())}
     if rank == 0:
         pairs = m * n
         tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
@@ -402,17 +581,24 @@ def run_fused_nn_multi(args):
                 "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops_sustained x n_gpus)",
                 "kernel": "screen_tc_kernel (tcgen05, 1-product screen) + expanded_tc_kernel (EPI_MINLOC, exact on 1/32 of "
                           "the db blocks and wherever screening is called off); algorithmic 2mnk FLOP / time",
-                "traffic": None}
+                "traffic": ncu_traffic("screen_tc_per_launch")}
         roof["frac"] = roof["achieved"] / roof["peak"]
+        cb, _, _ = cpu_baseline("fused_l2_nn", seconds_budget=8.0)
+        from raft_b200.distance.fused_l2_nn import plan_exchanges
+        n_calls = len(plan_exchanges(n // world, world))
         line = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "scaling_record": {"t1_ms": t1_ms, "tN_ms": ms, "speedup": (t1_ms / ms) if t1_ms else None,
+                                   "efficiency": (t1_ms / ms / world) if t1_ms else None,
+                                   "note": "t1 = the same job un-sharded on rank 0's GPU, same session, same data"},
                 "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic make_blobs-like (5 centres U[-10,10]^k, sigma 1), generated on device",
                 "config": {"workload": "fusedL2NN 1000000 queries x 8000000 db x 96 fp32, db row-sharded",
-                           "parallelism": f"db_shard{world}", "exchange": "2 x all_reduce(int64 MIN) of 1M packed (dist,idx) keys (bounds after a 32768-row head, result at the end)",
+                           "parallelism": f"db_shard{world}",
+                           "exchange": f"{n_calls} x all_reduce(int64 MIN) of 1M packed (dist,idx) keys per step (bounds between sub-chunks of the shard, result at the end)",
                            "l2": "db shard + queries exceed L2 for world<=8 (>=768 MB per rank)"},
-                "roofline": roof, "cpu_baseline": None,
-                "e2e": None, "gpu_launches": nn_launches(hi - lo, world) * args.steps, "clocks": cs.summary(),
+                "roofline": roof, "parity": parity, "cpu_baseline": cb,
+                "e2e": None, "gpu_launches": nn_launches(n // world, world) * args.steps, "clocks": cs.summary(),
                 "ms_per_step_all": [round(v, 3) for v in per]}
     # e2e needs every rank to take part in the collective
     qh = q.cpu().pin_memory()
@@ -422,7 +608,7 @@ def run_fused_nn_multi(args):
         with torch.cuda.stream(h.torch_stream):
             q.copy_(qh, non_blocking=True)
             db.copy_(dbh, non_blocking=True)
-        i, v = fused_l2_nn_sharded(q, db, lo, sqrt=False, handle=h, keys=keys)
+        i, v = fused_l2_nn_sharded(q, db, lo, sqrt=False, handle=h, keys=keys, n_total=n)
         return i.cpu(), v.cpu()
 
     e2e_step()

@@ -1,17 +1,28 @@
 // Minimal stand-in for the parts of raft/core that the distance shim needs, used ONLY when the real
 // RAFT headers are not on the include path (RMM / CCCL 3 are not installable offline; SURVEY.md
-// hard part F).  With real RAFT present, define RAFT_B200_USE_REAL_RAFT and include
-// <raft/core/resources.hpp>, <raft/core/device_mdspan.hpp>, <raft/core/kvp.hpp>, <raft/core/error.hpp>
-// before the distance headers: the shim only uses the names below, with the reference's semantics.
+// hard part F).  With real RAFT present, define RAFT_B200_USE_REAL_RAFT: the shim then includes
+// <raft/core/resources.hpp>, <raft/core/resource/cuda_stream.hpp>, <raft/core/device_mdspan.hpp>,
+// <raft/core/kvp.hpp>, <raft/core/error.hpp> itself and this file defines nothing
+// (tests/test_cpp_shim.py compiles that configuration against tests/cpp/mock_raft, a header tree with the
+// reference's signatures and NO members beyond them).
 //
 //   raft::resources + raft::resource::get_cuda_stream   cpp/include/raft/core/resources.hpp:38-128,
 //                                                       cpp/include/raft/core/resource/cuda_stream.hpp:58-64
-//   workspace memory resource                           cpp/include/raft/core/resource/device_memory_resource.hpp:100-129
-//   raft::device_matrix_view / make_device_matrix_view   cpp/include/raft/core/device_mdspan.hpp:94-97,169-176
+//   raft::row_major / col_major / device_matrix_view     cpp/include/raft/core/mdspan_types.hpp:19-32,
+//                                                       cpp/include/raft/core/device_mdspan.hpp:94-97,169-176
+//                                                       (aliases of cuda::std::mdspan, as here)
 //   raft::KeyValuePair                                  cpp/include/raft/core/kvp.hpp:20-62
 //   raft::logic_error / raft::cuda_error / RAFT_EXPECTS cpp/include/raft/core/error.hpp:218-239
+// Temporaries: include/raft/core/b200_workspace.hpp (the counterpart of the handle's workspace resource).
 #pragma once
-#ifndef RAFT_B200_USE_REAL_RAFT
+#ifdef RAFT_B200_USE_REAL_RAFT
+#include <raft/core/device_mdspan.hpp>
+#include <raft/core/error.hpp>
+#include <raft/core/kvp.hpp>
+#include <raft/core/resource/cuda_stream.hpp>
+#include <raft/core/resources.hpp>
+#else
+#include <cuda/std/mdspan>
 #include <cuda_runtime_api.h>
 #include <cstddef>
 #include <cstdint>
@@ -29,27 +40,33 @@ struct cuda_error : exception { using exception::exception; };
     if (!(cond)) throw ::raft::logic_error(std::string("RAFT failure: ") + (msg)); \
   } while (0)
 
-struct row_major {};
-struct col_major {};
+using cuda::std::dynamic_extent;
+using cuda::std::extents;
+using cuda::std::layout_left;
+using cuda::std::layout_right;
+using cuda::std::layout_stride;
+using row_major = layout_right;
+using col_major = layout_left;
+template <typename IndexType>
+using matrix_extent = cuda::std::extents<IndexType, dynamic_extent, dynamic_extent>;
 
-// device_matrix_view<T, IdxT, Layout>: data_handle() + extent(i), like the mdspan alias it replaces
-template <typename T, typename IdxT = int, typename Layout = row_major>
-class device_matrix_view {
- public:
-  using element_type = T;
-  using index_type   = IdxT;
-  using layout_type  = Layout;
-  device_matrix_view(T* p, IdxT rows, IdxT cols) : p_(p), r_(rows), c_(cols) {}
-  T* data_handle() const { return p_; }
-  IdxT extent(int i) const { return i == 0 ? r_ : c_; }
- private:
-  T* p_;
-  IdxT r_, c_;
-};
-template <typename T, typename IdxT = int, typename Layout = row_major>
-device_matrix_view<T, IdxT, Layout> make_device_matrix_view(T* p, IdxT rows, IdxT cols)
+// device_matrix_view<T, IdxT, Layout>: a 2-d cuda::std::mdspan (the reference adds an accessor that tags the
+// memory as device memory; data_handle() / extent(i) / stride(i) are what the shim uses)
+template <typename T, typename IdxT = std::uint32_t, typename Layout = row_major>
+using device_matrix_view = cuda::std::mdspan<T, matrix_extent<IdxT>, Layout>;
+
+template <typename T, typename IdxT = std::uint32_t, typename Layout = row_major>
+auto constexpr make_device_matrix_view(T* p, IdxT rows, IdxT cols)
 {
-  return device_matrix_view<T, IdxT, Layout>(p, rows, cols);
+  return device_matrix_view<T, IdxT, Layout>{p, matrix_extent<IdxT>{rows, cols}};
+}
+// row-major view with a leading dimension (raft::make_device_strided_matrix_view, device_mdspan.hpp:178-199)
+template <typename T, typename IdxT = std::uint32_t>
+auto make_device_strided_matrix_view(T* p, IdxT rows, IdxT cols, IdxT ld)
+{
+  cuda::std::array<IdxT, 2> strides{ld, IdxT(1)};
+  return device_matrix_view<T, IdxT, layout_stride>{
+    p, typename layout_stride::template mapping<matrix_extent<IdxT>>{matrix_extent<IdxT>{rows, cols}, strides}};
 }
 
 template <typename K, typename V>
@@ -58,37 +75,23 @@ struct KeyValuePair {
   V value;
 };
 
-// raft::resources: a stream plus a grow-only workspace (the default workspace resource of the
-// reference is a pool limited to 1/4 of device memory; here: cudaMallocAsync on the handle's stream)
+// raft::resources: here just the stream (the reference keeps every resource behind get_*() free functions)
 class resources {
  public:
   explicit resources(cudaStream_t s = nullptr) : stream_(s) {}
   resources(const resources&) = delete;
-  ~resources() { if (ws_) cudaFreeAsync(ws_, stream_); }
-  cudaStream_t stream() const { return stream_; }
-  void* workspace(std::size_t bytes) const
-  {
-    if (bytes > ws_bytes_) {
-      if (ws_) cudaFreeAsync(ws_, stream_);
-      if (cudaMallocAsync(&ws_, bytes, stream_) != cudaSuccess) throw cuda_error("workspace allocation failed");
-      ws_bytes_ = bytes;
-    }
-    return ws_;
-  }
-  std::size_t workspace_bytes() const { return ws_bytes_; }
+  cudaStream_t b200_stream() const { return stream_; }
  private:
   cudaStream_t stream_;
-  mutable void* ws_              = nullptr;
-  mutable std::size_t ws_bytes_ = 0;
 };
 using device_resources = resources;
 using handle_t         = resources;
 
 namespace resource {
-inline cudaStream_t get_cuda_stream(resources const& h) { return h.stream(); }
+inline cudaStream_t get_cuda_stream(resources const& h) { return h.b200_stream(); }
 inline void sync_stream(resources const& h)
 {
-  if (cudaStreamSynchronize(h.stream()) != cudaSuccess) throw cuda_error("cudaStreamSynchronize failed");
+  if (cudaStreamSynchronize(get_cuda_stream(h)) != cudaSuccess) throw cuda_error("cudaStreamSynchronize failed");
 }
 }  // namespace resource
 }  // namespace raft

@@ -30,10 +30,11 @@ void fused_l2_knn(raft::resources const& handle, raft::device_matrix_view<const 
   const int64_t m = query.extent(0), n = index.extent(0), d = index.extent(1), k = out_inds.extent(1);
   const size_t need = b2d_knn_l2_workspace_bytes(m, n, d, k);
   if (need == static_cast<size_t>(-1)) throw raft::logic_error("fused_l2_knn: k must be in [1, 64]");
-  void* ws = handle.workspace(need);
+  raft::b200::scoped_workspace ws(handle, need);
   raft::distance::detail::b2d_check(b2d_knn_l2(raft::resource::get_cuda_stream(handle),
                                                reinterpret_cast<int64_t*>(out_inds.data_handle()), out_dists.data_handle(),
-                                               query.data_handle(), d, index.data_handle(), d, m, n, d, k, rt ? 1 : 0, ws, need));
+                                               query.data_handle(), d, index.data_handle(), d, m, n, d, k, rt ? 1 : 0,
+                                               ws.data(), need));
 }
 
 // single-partition form of brute_force::knn (the reference's vector-of-partitions overload merged

@@ -17,7 +17,8 @@ DataT silhouette_score(raft::resources const& handle, const DataT* X_in, int nRo
   static_assert(std::is_same<DataT, float>::value && sizeof(LabelT) == 4, "raft_b200: silhouette_score is provided for <float, int>");
   const size_t need = b2d_silhouette_score_workspace_bytes(nRows, nCols, nLabels, static_cast<int>(metric), chunk);
   if (need == static_cast<size_t>(-1)) throw raft::logic_error("silhouette_score: metric not supported");
-  char* ws = static_cast<char*>(handle.workspace(need + 256));
+  raft::b200::scoped_workspace scratch(handle, need + 256);
+  char* ws       = static_cast<char*>(scratch.data());
   float* d_score = reinterpret_cast<float*>(ws);
   raft::distance::detail::b2d_check(b2d_silhouette_score(stream, d_score, silhouette_scorePerSample, X_in, nCols,
                                                          reinterpret_cast<const int*>(labels), nRows, nCols, nLabels,

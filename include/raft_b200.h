@@ -81,6 +81,14 @@ typedef struct {
 enum { B2D_L0PseudoNorm = 0, B2D_L1Norm = 1, B2D_L2Norm = 2, B2D_LinfNorm = 3 };
 
 int b2d_version(void);
+/* Process-wide tuning / test hooks (nothing on the hot path reads the environment):
+ *   "nn_screen"  0 forces the exact arg-min kernel for fusedL2NN (default 1: screened search where it applies)
+ *   "nn_tau"     candidates per row above which the trial pass calls screening off (default 6) */
+int b2d_set_option(const char* name, double value);
+/* Diagnostic -- SYNCHRONISES `stream`: control words of the last screened fusedL2NN chunk in `workspace`:
+ * [0] candidates incl. one incumbent per row, [1] list overflow, [2] go_screen, [3] go_exact, [4] redo_trial,
+ * [5] candidates after the trial pass. */
+int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out6);
 /* thread-local description of the last non-zero status returned on this thread */
 const char* b2d_last_error(void);
 
@@ -129,6 +137,20 @@ int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
 int b2d_fused_l2_nn_finalize(void* stream, b2d_kvp_if* out, const int64_t* keys, int64_t m,
                              int do_sqrt, const void* workspace, size_t workspace_bytes);
 
+/* Single-process multi-GPU fusedL2NN (the reference's SNMG pattern: one ncclComm_t per device from a
+ * grouped ncclCommInitRank / ncclCommInitAll, cpp/include/raft/core/resource/nccl_comm.hpp:43-62,
+ * cpp/include/raft/core/device_resources_snmg.hpp:35-154).  Device g holds the replicated queries x[g] [m,k], its
+ * database row block y[g] [n_shard[g],k] (global index of its first row: idx_offset[g]), keys[g] [m] and a workspace of
+ * b2d_fused_l2_nn_workspace_bytes(m, n_shard[g], k) bytes; streams[g] is a cudaStream_t of device devices[g] and
+ * comms[g] the ncclComm_t of that device (NULL array allowed for ngpu == 1).  Work is only enqueued: per exchange
+ * step one ncclAllReduce(int64, min) of the m packed keys per device inside a ncclGroupStart/End (a 32768-row head of
+ * every shard, then sub-chunks growing x4: the screened search starts each from GLOBAL bounds), then out[g] [m] is
+ * written on every device (identical results).  NCCL is resolved at run time from the libnccl.so.2 already loaded. */
+int b2d_fused_l2_nn_multi(int ngpu, const int* devices, void* const* streams, void* const* comms, b2d_kvp_if* const* out,
+                          const float* const* x, int64_t ldx, const float* const* y, int64_t ldy, const int64_t* n_shard,
+                          const int64_t* idx_offset, int64_t m, int64_t k, int do_sqrt, int64_t* const* keys,
+                          void* const* workspace, const size_t* workspace_bytes);
+
 /* Fused brute-force kNN for the L2 metrics (replaces raft::neighbors::brute_force::knn /
  * fused_l2_knn, removed with the distance package -- CHANGELOG.md:59-60 -- and the pair
  * pairwise_distance + raft::matrix::select_k, cpp/include/raft/matrix/select_k.cuh:73-106):
@@ -151,7 +173,8 @@ int b2d_knn_l2(void* stream, int64_t* out_idx, float* out_dist, const float* x, 
  * per_sample (device, [n]) optional.  labels: int32 in [0, n_labels).  metric: any metric of
  * b2d_pairwise_distance (the reference's default is L2Unexpanded).  The n x n matrix is produced and
  * consumed in [chunk_rows x n] slabs (0 = about 1 GiB per slab), like the reference's batched variant
- * (detail/batched/silhouette_score.cuh:213-243).  Synchronises the stream once (label validation). */
+ * (detail/batched/silhouette_score.cuh:213-243).  Never synchronises: labels are validated on the device, a label
+ * outside [0, n_labels) makes *score (and the per-sample value of that row) NaN. */
 size_t b2d_silhouette_score_workspace_bytes(int64_t n, int64_t k, int n_labels, int metric, int64_t chunk_rows);
 int b2d_silhouette_score(void* stream, float* score, float* per_sample, const float* x, int64_t ldx,
                          const int* labels, int64_t n, int64_t k, int n_labels, int metric, float metric_arg,
@@ -159,12 +182,13 @@ int b2d_silhouette_score(void* stream, float* score, float* per_sample, const fl
 
 /* raft::stats::trustworthiness_score (cpp/include/raft/stats/detail/trustworthiness_score.cuh:113-211), the
  * other dangling caller: x [n, m] original space, x_embedded [n, d]; neighbours in the
- * embedded space from the fused kNN (L2), ranks in the original space (`metric`: any metric of
- * b2d_pairwise_distance) counted over [batch_rows x n] slabs (0 = about 1 GiB).  *score_host is a HOST
- * double; the call synchronises the stream.  n_neighbors <= 63. */
+ * embedded space from the fused kNN and ranks in the original space both under `metric` (the reference's
+ * distance_type template parameter; L2 / L2Sqrt (Expanded or Unexpanded), CosineExpanded, CorrelationExpanded),
+ * ranks counted over [batch_rows x n] slabs (0 = about 1 GiB).  *score is a DEVICE double; the call never
+ * synchronises.  n_neighbors <= 63. */
 size_t b2d_trustworthiness_score_workspace_bytes(int64_t n, int64_t m, int64_t d, int n_neighbors, int metric,
                                                  int64_t batch_rows);
-int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, int64_t ldx,
+int b2d_trustworthiness_score(void* stream, double* score, const float* x, int64_t ldx,
                               const float* x_embedded, int64_t lde, int64_t n, int64_t m, int64_t d,
                               int n_neighbors, int metric, int64_t batch_rows, void* workspace,
                               size_t workspace_bytes);
@@ -180,6 +204,12 @@ int b2d_profile_end(float* ms, int max_count, int* count);
  * fin_op, cpp/include/raft/linalg/norm.cuh:118-147). */
 int b2d_row_norm(void* stream, float* out, const float* x, int64_t ldx, int64_t rows, int64_t k,
                  int norm_type, int do_sqrt);
+
+/* raft::matrix::argmin (cpp/include/raft/matrix/argmin.cuh:25-37; cpp/include/raft/matrix/detail/math.cuh:290-343):
+ * out[r] = column of the minimum of row r of in:[rows,n] (row pitch ld), ties -> smaller index, a row without any
+ * value below +inf (all NaN / +inf) -> 0.  The separate-pass form of the arg-min that fusedL2NN fuses;
+ * one read of the matrix. */
+int b2d_row_argmin(void* stream, int32_t* out, const float* in, int64_t ld, int64_t rows, int64_t n);
 
 #ifdef __cplusplus
 }

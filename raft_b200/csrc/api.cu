@@ -1,10 +1,12 @@
 // C-ABI entry points (include/raft_b200.h) and host-side dispatch.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -33,6 +35,10 @@ static int fail(int code, const std::string& msg)
   } while (0)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// process-wide tuning / test hooks (b2d_set_option): nothing on the hot path reads the environment
+static std::atomic<float> g_nn_tau{6.0f};   // screened fusedL2NN: candidates per row above which the trial calls screening off
+static std::atomic<int> g_nn_screen{1};     // 0: always the exact arg-min kernel
 
 // ------------------------------------------------------------------------------------------
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency, so the
@@ -122,6 +128,9 @@ struct TcWorkspace {
   __half* yop;
   float* xt;
   float* yt;
+  float* xsc;        // [m] per-row scale 2^(E - e_row) of x (1 unless the row took its own exponent, prep.cuh)
+  float* ysc;        // [n] the same for y
+  unsigned* nonuni;  // [2] some row of x / y took its own exponent
   long long* keys;
   unsigned* gmax;  // [2]
   float* coef;     // [1]
@@ -146,10 +155,12 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   TcWorkspace w;
   // scalars, xt and keys come first so that their offsets depend on m only
   // (b2d_fused_l2_nn_finalize finds |x_i|^2 again without knowing n or k)
-  w.gmax = reinterpret_cast<unsigned*>(c + take(16));
+  w.gmax = reinterpret_cast<unsigned*>(c + take(32));
   w.coef = reinterpret_cast<float*>(w.gmax + 2);
   w.has_lo = w.gmax + 3;
+  w.nonuni = w.gmax + 4;
   w.xt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4));
+  w.xsc  = reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4));
   w.keys = reinterpret_cast<long long*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
   // screened fusedL2NN scratch: thresholds, counters, candidate list (128 per row and 1M-row chunk of y;
   // ~54 measured on far-from-origin clusters; overflow falls back to the exact pass on the device,
@@ -159,6 +170,7 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 32 : 0));
   w.cand     = reinterpret_cast<int2*>(c + take(static_cast<size_t>(w.cand_cap) * 8));
   w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
+  w.ysc  = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
   w.xop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(m) * nkb * 128));
   w.yop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(n) * nkb * 128));
   w.bytes = off;
@@ -184,12 +196,12 @@ static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int6
                        int mode, int center, int xform = 0, float coef_mul = 1.f, float tx_const = 0.f)
 {
   PrepParams p;
-  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, xn};
-  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, yn};
+  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, w.xsc, xn};
+  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, w.ysc, yn};
   p.k = static_cast<int>(k); p.nkb = static_cast<int>((k + 31) / 32); p.mode = mode; p.center = center;
-  p.gmax = w.gmax; p.coef = w.coef; p.has_lo = w.has_lo;
+  p.gmax = w.gmax; p.coef = w.coef; p.has_lo = w.has_lo; p.nonuni = w.nonuni;
   p.xform = xform; p.coef_mul = coef_mul; p.tx_const = tx_const;
-  B2D_CUDA(cudaMemsetAsync(w.gmax, 0, 16, s));
+  B2D_CUDA(cudaMemsetAsync(w.gmax, 0, 32, s));
   const int64_t blocks = (m + n + 7) / 8;
   prep_max_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
   B2D_CUDA(cudaGetLastError());
@@ -198,17 +210,24 @@ static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int6
   return B2D_OK;
 }
 
-// dist [m][n] fp32 (row pitch ldd), box = 32 x 32, SWIZZLE_128B (inner box = 128 bytes)
-static int make_dist_map(CUtensorMap* map, const float* base, int64_t m, int64_t n, int64_t ldd)
+// dist [m][n] fp32 (row pitch ldd) seen as [m][chunks of 128 columns][128]: box {132, 2, 8} = 8 rows x 2 chunks, the
+// 4 trailing floats of every chunk fall outside dimension 0 and are never written (padded smem rows, see
+// expanded_tc.cuh).  `first_col`/`cols`: the column range the map covers (the ragged last chunk has its own map).
+static int make_dist_map3(CUtensorMap* map, const float* base, int64_t m, int64_t first_col, int64_t cols, int64_t ldd)
 {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  cuuint64_t dims[2]    = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldd) * 4};
-  cuuint32_t box[2]     = {32, 32};
-  cuuint32_t estr[2]    = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+  const cuuint64_t inner = cols >= 128 ? 128 : static_cast<cuuint64_t>(cols);
+  cuuint64_t dims[3]    = {inner, static_cast<cuuint64_t>(cols >= 128 ? cols / 128 : 1), static_cast<cuuint64_t>(m)};
+  cuuint64_t strides[2] = {512, static_cast<cuuint64_t>(ldd) * 4};
+#if B2D_STG_MODE == 8
+  cuuint32_t box[3]     = {132, 2, 4};
+#else
+  cuuint32_t box[3]     = {132, 2, 8};
+#endif
+  cuuint32_t estr[3]    = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base + first_col), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(dist) failed: " + std::to_string((int)r));
   return B2D_OK;
@@ -216,23 +235,23 @@ static int make_dist_map(CUtensorMap* map, const float* base, int64_t m, int64_t
 
 template <bool kRes, int kEpi, int kPost, bool kTma>
 static int launch_tc_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                          const TcParams& p, int grid)
+                          const CUtensorMap& mr, const TcParams& p, int grid)
 {
   // the attribute is per device and per function: cheap, set on every launch
   B2D_CUDA(cudaFuncSetAttribute(expanded_tc_kernel<kRes, kEpi, kPost, kTma>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM_BYTES)));
-  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, p);
+  expanded_tc_kernel<kRes, kEpi, kPost, kTma><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mb, md, mr, p);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
 
 template <bool kRes, bool kTma>
 static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                           const TcParams& p, int grid, int post)
+                           const CUtensorMap& mr, const TcParams& p, int grid, int post)
 {
-  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, kTma>(s, ma, mb, md, p, grid);
-  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, kTma>(s, ma, mb, md, p, grid);
-  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, kTma>(s, ma, mb, md, p, grid);
+  if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, kTma>(s, ma, mb, md, mr, p, grid);
+  if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, kTma>(s, ma, mb, md, mr, p, grid);
+  return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, kTma>(s, ma, mb, md, mr, p, grid);
 }
 
 static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post, int kb0 = 0,
@@ -259,9 +278,13 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   p.yt       = w.yt;
   p.coef     = w.coef;
   p.has_lo   = w.has_lo;
+  p.xsc      = w.xsc;
+  p.ysc      = w.ysc;
+  p.nonuni   = w.nonuni;
   if (p.n_items == 0) return B2D_OK;
-  CUtensorMap ma, mb, md;
+  CUtensorMap ma, mb, md, mr;
   memset(&md, 0, sizeof(md));
+  memset(&mr, 0, sizeof(mr));
   rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM, kb0, nkb_total);
   if (rc) return rc;
   rc = make_operand_map(&mb, w.yop, p.n, p.nkb, TC_BN, kb0, nkb_total);
@@ -269,26 +292,49 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   const int grid      = static_cast<int>(p.n_items < sms ? p.n_items : sms);
   const bool resident = p.nkb <= TC_MAX_RES_KB;
   if (epi == EPI_MINLOC) {
-    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid)
-                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, p, grid);
+    return resident ? launch_tc_inst<true, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, mr, p, grid)
+                    : launch_tc_inst<false, EPI_MINLOC, POST_NONE, false>(s, ma, mb, md, mr, p, grid);
   }
   if (epi == EPI_TOPK) {
-    return resident ? launch_tc_inst<true, EPI_TOPK, POST_NONE, false>(s, ma, mb, md, p, grid)
-                    : launch_tc_inst<false, EPI_TOPK, POST_NONE, false>(s, ma, mb, md, p, grid);
+    return resident ? launch_tc_inst<true, EPI_TOPK, POST_NONE, false>(s, ma, mb, md, mr, p, grid)
+                    : launch_tc_inst<false, EPI_TOPK, POST_NONE, false>(s, ma, mb, md, mr, p, grid);
   }
-  // TMA tensor store needs a 16-byte aligned base and row pitch; its edge clipping works in 16-byte
-  // units (measured: with n % 4 != 0 it spills up to 3 floats into the row padding), so ragged or
-  // unaligned outputs take the direct register->global path
+  // bulk row stores (cp.async.bulk shared -> global) need 16-byte aligned addresses and sizes, i.e. a
+  // 16-byte aligned base and row pitch and n % 4 == 0; ragged or unaligned outputs take the direct
+  // register->global path
   bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0) &&
              p.acc_mode == 0;  // the K-chunked read-modify-write epilogue lives in the direct path
+#if B2D_STG_MODE == 0 || B2D_STG_MODE == 7 || B2D_STG_MODE == 8
   if (tma) {
-    rc = make_dist_map(&md, p.dist, p.m, p.n, p.ldd);
-    if (rc) return rc;
-    return resident ? launch_tc_store<true, true>(s, ma, mb, md, p, grid, post)
-                    : launch_tc_store<false, true>(s, ma, mb, md, p, grid, post);
+    // dist [m][n] fp32 (row pitch ldd), box = 32 x 32, SWIZZLE_128B (inner box = 128 bytes); edge clipping works in
+    // 16-byte units, hence n % 4 == 0 above
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t dims[2]    = {static_cast<cuuint64_t>(p.n), static_cast<cuuint64_t>(p.m)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(p.ldd) * 4};
+    cuuint32_t box[2]     = {32, 32};
+    cuuint32_t estr[2]    = {1, 1};
+    CUresult r = enc(&md, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.dist, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(dist) failed: " + std::to_string((int)r));
+    mr = md;
+#if B2D_STG_MODE == 7 || B2D_STG_MODE == 8
+    if (p.n >= 128) { rc = make_dist_map3(&mr, p.dist, p.m, 0, p.n / 128 * 128, p.ldd); if (rc) return rc; }
+#endif
+    return resident ? launch_tc_store<true, true>(s, ma, mb, md, mr, p, grid, post)
+                    : launch_tc_store<false, true>(s, ma, mb, md, mr, p, grid, post);
   }
-  return resident ? launch_tc_store<true, false>(s, ma, mb, md, p, grid, post)
-                  : launch_tc_store<false, false>(s, ma, mb, md, p, grid, post);
+#endif
+  if (tma) {
+    const int64_t full = p.n / 128 * 128;
+    if (full > 0) { rc = make_dist_map3(&md, p.dist, p.m, 0, full, p.ldd); if (rc) return rc; }
+    if (p.n > full) { rc = make_dist_map3(&mr, p.dist, p.m, full, p.n - full, p.ldd); if (rc) return rc; }
+    if (full == 0) md = mr;  // (never addressed inside the matrix: every box of the main map is out of range)
+    return resident ? launch_tc_store<true, true>(s, ma, mb, md, mr, p, grid, post)
+                    : launch_tc_store<false, true>(s, ma, mb, md, mr, p, grid, post);
+  }
+  return resident ? launch_tc_store<true, false>(s, ma, mb, md, mr, p, grid, post)
+                  : launch_tc_store<false, false>(s, ma, mb, md, mr, p, grid, post);
 }
 
 // coarse screening pass of the screened fusedL2NN (screen_tc.cuh) over the y blocks with
@@ -318,6 +364,7 @@ static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_
   p.chunk    = static_cast<int>(chunk);
   p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
   p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
+  p.xsc = w.xsc; p.nonuni = w.nonuni;
   p.yt = w.yt; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
   p.overflow = overflow; p.run_flag = run_flag; p.unit_norm = unit_norm;
   if (p.n_items == 0) return B2D_OK;
@@ -401,6 +448,62 @@ __global__ void row_norm_kernel(float* out, const float* x, int64_t ldx, int64_t
   }
 }
 
+// raft::matrix::argmin (cpp/include/raft/matrix/argmin.cuh:25-37, detail/math.cuh:290-343): column index of the
+// minimum of every row, ties -> the smaller index (cub::ArgMin), start value (0, +inf): a row of NaN / +inf gives 0.
+// One pass over the matrix: HBM-read bound.  kWarp: one warp per row (short rows), else one 256-thread block per row.
+template <bool kWarp>
+__global__ void __launch_bounds__(256) row_argmin_kernel(int* out, const float* in, int64_t ld, int64_t rows, int64_t n)
+{
+  const int lane    = threadIdx.x & 31;
+  const int64_t r   = kWarp ? static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5) : blockIdx.x;
+  const int t0      = kWarp ? lane : threadIdx.x;
+  const int stride  = kWarp ? 32 : 256;
+  float v = __int_as_float(0x7f800000);
+  int ix  = 0;
+  if (r < rows) {
+    const float* row = in + r * ld;
+    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0 && (ld & 3) == 0) {
+      const int64_t n4 = n >> 2;
+      for (int64_t c = t0; c < n4; c += stride) {
+        const float4 q4 = __ldcs(reinterpret_cast<const float4*>(row) + c);
+        const int j     = static_cast<int>(c << 2);
+        if (q4.x < v) { v = q4.x; ix = j; }
+        if (q4.y < v) { v = q4.y; ix = j + 1; }
+        if (q4.z < v) { v = q4.z; ix = j + 2; }
+        if (q4.w < v) { v = q4.w; ix = j + 3; }
+      }
+      for (int64_t c = (n4 << 2) + t0; c < n; c += stride) {
+        const float q1 = __ldcs(row + c);
+        if (q1 < v) { v = q1; ix = static_cast<int>(c); }
+      }
+    } else {
+      for (int64_t c = t0; c < n; c += stride) {
+        const float q1 = __ldcs(row + c);
+        if (q1 < v) { v = q1; ix = static_cast<int>(c); }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi   = __shfl_xor_sync(0xffffffffu, ix, o);
+    if (ov < v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+  }
+  if (kWarp) {
+    if (lane == 0 && r < rows) out[r] = ix;
+    return;
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  if (lane == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = ix; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] < v || (sv[w] == v && si[w] < ix)) { v = sv[w]; ix = si[w]; }
+    out[r] = ix;
+  }
+}
+
 }  // namespace b2d
 
 using namespace b2d;
@@ -436,7 +539,33 @@ int b2d_profile_end(float* ms, int max_count, int* count)
 }
 
 
-int b2d_version(void) { return 100; }
+int b2d_version(void) { return 200; }
+
+int b2d_set_option(const char* name, double value)
+{
+  if (!name) return fail(B2D_ERR_INVALID_ARG, "null option name");
+  const std::string n(name);
+  if (n == "nn_tau") {
+    if (!(value >= 0.0)) return fail(B2D_ERR_INVALID_ARG, "nn_tau must be >= 0");
+    g_nn_tau.store(static_cast<float>(value));
+  } else if (n == "nn_screen") {
+    g_nn_screen.store(value != 0.0 ? 1 : 0);
+  } else {
+    return fail(B2D_ERR_INVALID_ARG, "unknown option '" + n + "' (nn_tau, nn_screen)");
+  }
+  return B2D_OK;
+}
+
+// Diagnostic (synchronises `stream`): the control words the last screened fusedL2NN chunk left in `workspace`
+// [0] candidates (incl. one incumbent per row) [1] list overflow [2] go_screen [3] go_exact [4] redo_trial [5] candidates after the trial
+int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out6)
+{
+  if (!workspace || !out6 || m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "null workspace / out");
+  TcWorkspace w = tc_layout(const_cast<void*>(workspace), m, n, k, true);
+  B2D_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  B2D_CUDA(cudaMemcpy(out6, w.cand_cnt, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return B2D_OK;
+}
 const char* b2d_last_error(void) { return g_err.c_str(); }
 
 size_t b2d_pairwise_workspace_bytes(int metric, int dtype, int64_t m, int64_t n, int64_t k)
@@ -468,7 +597,8 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
   if (dtype != B2D_F32 && dtype != B2D_F16) return fail(B2D_ERR_UNSUPPORTED, "dtype");
   if (metric == B2D_LpUnexpanded && !(metric_arg > 0.f)) return fail(B2D_ERR_INVALID_ARG, "LpUnexpanded needs p > 0");
 
-  // Fortran order: D^T (row-major [n,m]) = metric(y_j, x_i); all metrics here are symmetric.
+  // Fortran order: D^T (row-major [n,m]) = metric(y_j, x_i).  Every metric here is symmetric except
+  // KLDivergence, which switches to the kernel with the operand roles exchanged (UX_KL_REV).
   const void *xa = x, *ya = y;
   int64_t ma = m, na = n;
   int64_t xrs, xcs, yrs, ycs;
@@ -539,7 +669,8 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     case B2D_Linf: return launch_ux_inst<UX_LINF>(s, p, tiles);
     case B2D_Canberra: return launch_ux_inst<UX_CANBERRA>(s, p, tiles);
     case B2D_HammingUnexpanded: return launch_ux_inst<UX_HAMMING>(s, p, tiles);
-    case B2D_KLDivergence: return launch_ux_inst<UX_KL>(s, p, tiles);
+    case B2D_KLDivergence:
+      return row_major ? launch_ux_inst<UX_KL>(s, p, tiles) : launch_ux_inst<UX_KL_REV>(s, p, tiles);
     case B2D_JensenShannon: return launch_ux_inst<UX_JS>(s, p, tiles);
     default: return launch_ux_inst<UX_LP>(s, p, tiles);
   }
@@ -581,7 +712,7 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   //                                                            where screening was called off)
   // Every launch after T is conditional on a device flag: no host round trip, no wrong answer.
   constexpr int kSel = 32;
-  static const float tau = getenv("B2D_NN_TAU") ? static_cast<float>(atof(getenv("B2D_NN_TAU"))) : 6.0f;
+  const float tau = g_nn_tau.load(std::memory_order_relaxed);
   unsigned* flags = w.cand_cnt;  // [0] count [1] overflow [2] go_screen [3] go_exact [4] redo_trial [5] count after T
   p.sel_s = kSel; p.sel_lo = 0; p.sel_hi = 1;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
@@ -591,11 +722,11 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   B2D_CUDA(cudaGetLastError());
   rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr, unit_norm);
   if (rc) return rc;
-  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 1);
+  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 1, w.nonuni);
   B2D_CUDA(cudaGetLastError());
   rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2, unit_norm);
   if (rc) return rc;
-  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 2);
+  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 2, w.nonuni);
   B2D_CUDA(cudaGetLastError());
   int sms = 0, cc = 0;
   rc = device_sms(&sms, &cc);
@@ -609,13 +740,6 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   p.sel_lo = 2; p.sel_hi = kSel; p.run_flag = flags + 3;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
-  if (getenv("B2D_NN_DEBUG")) {  // diagnostics only: synchronises
-    unsigned h[6];
-    cudaStreamSynchronize(s);
-    cudaMemcpy(h, flags, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "b2d nn: candidates %u (%.2f/row; after trial %.3f/row) overflow %u go_screen %u go_exact %u redo_trial %u\n",
-            h[0], double(h[0]) / m - 1.0, double(h[5]) / m - 1.0, h[1], h[2], h[3], h[4]);
-  }
   return B2D_OK;
 }
 
@@ -634,7 +758,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   if (!workspace || workspace_bytes < need)
     return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
   if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(B2D_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
-  static const bool screen_off = getenv("B2D_NN_SCREEN") != nullptr && atoi(getenv("B2D_NN_SCREEN")) == 0;
+  const bool screen_off = g_nn_screen.load(std::memory_order_relaxed) == 0;
   if (init_keys) {
     minloc_init_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), m);
     B2D_CUDA(cudaGetLastError());
@@ -700,6 +824,93 @@ int b2d_fused_l2_nn(void* stream, b2d_kvp_if* out, const float* x, int64_t ldx, 
   return B2D_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-process multi-GPU fusedL2NN: the reference's SNMG pattern -- one ncclComm_t per device,
+// created by the caller with a grouped ncclCommInitRank / ncclCommInitAll
+// (cpp/include/raft/core/resource/nccl_comm.hpp:43-62, core/device_resources_snmg.hpp:35-154).  NCCL is resolved at
+// run time (dlopen of the libnccl.so.2 the process already uses), so the library has no link-time NCCL dependency.
+namespace {
+struct NcclApi {
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*group_start)()                                                          = nullptr;
+  int (*group_end)()                                                            = nullptr;
+  const char* (*err_string)(int)                                                = nullptr;
+  bool ok                                                                       = false;
+};
+const NcclApi& nccl_api()
+{
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.all_reduce  = reinterpret_cast<decltype(api.all_reduce)>(dlsym(h, "ncclAllReduce"));
+    api.group_start = reinterpret_cast<decltype(api.group_start)>(dlsym(h, "ncclGroupStart"));
+    api.group_end   = reinterpret_cast<decltype(api.group_end)>(dlsym(h, "ncclGroupEnd"));
+    api.err_string  = reinterpret_cast<decltype(api.err_string)>(dlsym(h, "ncclGetErrorString"));
+    api.ok          = api.all_reduce && api.group_start && api.group_end;
+  });
+  return api;
+}
+constexpr int kNcclInt64 = 4, kNcclMin = 3;  // ncclInt64 / ncclMin of nccl.h (stable ABI values since NCCL 2.0)
+constexpr int64_t kShardHeadRows = 1 << 15;
+}  // namespace
+
+int b2d_fused_l2_nn_multi(int ngpu, const int* devices, void* const* streams, void* const* comms, b2d_kvp_if* const* out,
+                          const float* const* x, int64_t ldx, const float* const* y, int64_t ldy, const int64_t* n_shard,
+                          const int64_t* idx_offset, int64_t m, int64_t k, int do_sqrt, int64_t* const* keys,
+                          void* const* workspace, const size_t* workspace_bytes)
+{
+  if (ngpu < 1 || ngpu > 64) return fail(B2D_ERR_INVALID_ARG, "ngpu must be in [1, 64]");
+  if (!devices || !streams || !out || !x || !y || !n_shard || !idx_offset || !keys || !workspace || !workspace_bytes)
+    return fail(B2D_ERR_INVALID_ARG, "null argument array");
+  if (ngpu > 1 && !comms) return fail(B2D_ERR_INVALID_ARG, "null comms");
+  const NcclApi& nccl = nccl_api();
+  if (ngpu > 1 && !nccl.ok) return fail(B2D_ERR_CUDA, "NCCL (libnccl.so.2) could not be loaded");
+  int prev = 0;
+  B2D_CUDA(cudaGetDevice(&prev));
+  // exchange plan: identical on every device (it depends on the SMALLEST shard): a 32768-row head, then sub-chunks
+  // growing x4, one all-reduce of the packed keys after each (raft_b200/distance/fused_l2_nn.py: plan_exchanges)
+  int64_t smin = n_shard[0];
+  for (int g = 1; g < ngpu; ++g) smin = std::min(smin, n_shard[g]);
+  std::vector<int64_t> plan;
+  if (ngpu > 1 && smin > 0) {
+    int64_t left = smin, step = kShardHeadRows;
+    while (left > 4 * step && plan.size() < 3) { plan.push_back(step); left -= step; step *= 4; }
+    plan.push_back(left);
+  } else {
+    plan.push_back(smin);
+  }
+  std::vector<int64_t> done(ngpu, 0);
+  int rc = B2D_OK;
+  for (size_t c = 0; c < plan.size() && rc == B2D_OK; ++c) {
+    const bool last = c + 1 == plan.size();
+    for (int g = 0; g < ngpu && rc == B2D_OK; ++g) {
+      if (cudaSetDevice(devices[g]) != cudaSuccess) { rc = fail(B2D_ERR_CUDA, "cudaSetDevice failed"); break; }
+      const int64_t rows = last ? n_shard[g] - done[g] : std::min(plan[c], n_shard[g] - done[g]);
+      rc = b2d_fused_l2_nn_keys(streams[g], keys[g], x[g], ldx, y[g] + done[g] * ldy, ldy, nullptr, nullptr, m, rows, k,
+                                idx_offset[g] + done[g], c == 0 ? 1 : 0, workspace[g], workspace_bytes[g]);
+      done[g] += rows;
+    }
+    if (rc == B2D_OK && ngpu > 1) {
+      int st = nccl.group_start();
+      for (int g = 0; g < ngpu && st == 0; ++g)
+        st = nccl.all_reduce(keys[g], keys[g], static_cast<size_t>(m), kNcclInt64, kNcclMin, comms[g],
+                             static_cast<cudaStream_t>(streams[g]));
+      const int st2 = nccl.group_end();
+      if (st == 0) st = st2;
+      if (st != 0) rc = fail(B2D_ERR_CUDA, std::string("ncclAllReduce(int64, min): ") + (nccl.err_string ? nccl.err_string(st) : "error"));
+    }
+  }
+  for (int g = 0; g < ngpu && rc == B2D_OK; ++g) {
+    if (cudaSetDevice(devices[g]) != cudaSuccess) { rc = fail(B2D_ERR_CUDA, "cudaSetDevice failed"); break; }
+    rc = b2d_fused_l2_nn_finalize(streams[g], out[g], keys[g], m, do_sqrt, workspace[g], workspace_bytes[g]);
+  }
+  cudaSetDevice(prev);
+  return rc;
+}
+
 int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float* x, int64_t ldx, const float* y,
                           int64_t ldy, const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int init_out,
                           void* workspace, size_t workspace_bytes)
@@ -762,6 +973,7 @@ static int knn_pass(KnnCtx& c, int64_t off, int64_t width)
   TcWorkspace w2 = c.w;
   w2.yop         = c.w.yop + static_cast<size_t>(off) * c.nkb * 64;
   w2.yt          = c.w.yt + off;
+  w2.ysc         = c.w.ysc + off;
   TcParams p     = c.p;
   p.n            = width;
   p.idx_offset   = off;
@@ -813,6 +1025,8 @@ int b2d_knn(void* stream, int64_t* out_idx, float* out_dist, int metric, const f
   if (!out_idx || !out_dist || !x || !y) return fail(B2D_ERR_INVALID_ARG, "null out / x / y");
   if (ldx < k || ldy < k) return fail(B2D_ERR_INVALID_ARG, "leading dimension smaller than k");
   if (n > 0xFFFFFFFFll) return fail(B2D_ERR_INVALID_ARG, "index range exceeds 32 bits");
+  if (m * static_cast<int64_t>(KNN_CAP) > tc_layout(nullptr, m, n, k, true).cand_cap)
+    return fail(B2D_ERR_UNSUPPORTED, "kNN: too many query rows for one call (m * 128 must stay below 2^31): split the queries");
   const size_t need = b2d_knn_l2_workspace_bytes(m, n, k, n_neighbors);
   if (!workspace || workspace_bytes < need)
     return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
@@ -922,10 +1136,8 @@ int b2d_silhouette_score(void* stream, float* score, float* per_sample, const fl
   sil_scan_kernel<<<1, 32, 0, s>>>(counts, offsets, cursor, n_labels);
   sil_gather_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(x, ldx, labels, cursor, ys, where, n, static_cast<int>(k), n_labels);
   B2D_CUDA(cudaGetLastError());
-  unsigned h_bad = 0;
-  B2D_CUDA(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
-  B2D_CUDA(cudaStreamSynchronize(s));
-  if (h_bad) return fail(B2D_ERR_INVALID_ARG, "labels must lie in [0, n_labels)");
+  // labels outside [0, n_labels) are detected on the device (no host round trip: the call stays asynchronous);
+  // they poison the result: *score and the per-sample values of the offending rows become NaN
   for (int64_t r0 = 0; r0 < n; r0 += L.chunk) {
     const int64_t rows = std::min<int64_t>(L.chunk, n - r0);
     int rc = b2d_pairwise_distance(stream, metric, B2D_F32, x + r0 * ldx, ldx, ys, k, slab, L.ld, rows, n, k, 1, metric_arg,
@@ -935,7 +1147,7 @@ int b2d_silhouette_score(void* stream, float* score, float* per_sample, const fl
       slab, L.ld, r0, rows, labels, counts, offsets, where, n_labels, per_sample, total);
     B2D_CUDA(cudaGetLastError());
   }
-  sil_finish_kernel<<<1, 32, 0, s>>>(total, score, n);
+  sil_finish_kernel<<<1, 32, 0, s>>>(total, score, n, bad);
   B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
@@ -978,13 +1190,22 @@ size_t b2d_trustworthiness_score_workspace_bytes(int64_t n, int64_t m, int64_t d
   return trust_layout(n, m, d, n_neighbors, metric, batch_rows).bytes;
 }
 
-int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, int64_t ldx, const float* x_embedded,
+int b2d_trustworthiness_score(void* stream, double* score, const float* x, int64_t ldx, const float* x_embedded,
                               int64_t lde, int64_t n, int64_t m, int64_t d, int n_neighbors, int metric,
                               int64_t batch_rows, void* workspace, size_t workspace_bytes)
 {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n < 0 || m <= 0 || d <= 0 || batch_rows < 0) return fail(B2D_ERR_INVALID_ARG, "bad extent");
-  if (!score_host || !x || !x_embedded) return fail(B2D_ERR_INVALID_ARG, "null score / x / x_embedded");
+  if (!score || !x || !x_embedded) return fail(B2D_ERR_INVALID_ARG, "null score / x / x_embedded");
+  // the reference uses distance_type for BOTH spaces (trustworthiness_score<math_t, distance_type>,
+  // cpp/include/raft/stats/detail/trustworthiness_score.cuh:113-211): the embedded-space neighbours come from
+  // the fused kNN, which covers the L2 and the cosine families
+  int knn_metric = metric;
+  if (metric == B2D_L2Unexpanded) knn_metric = B2D_L2Expanded;
+  if (metric == B2D_L2SqrtUnexpanded) knn_metric = B2D_L2SqrtExpanded;
+  if (knn_metric != B2D_L2Expanded && knn_metric != B2D_L2SqrtExpanded && knn_metric != B2D_CosineExpanded &&
+      knn_metric != B2D_CorrelationExpanded)
+    return fail(B2D_ERR_UNSUPPORTED, "trustworthiness_score supports the L2 metrics, CosineExpanded and CorrelationExpanded");
   if (n_neighbors < 1 || n_neighbors + 1 > KNN_MAX_K) return fail(B2D_ERR_UNSUPPORTED, "n_neighbors must be in [1, 63]");
   if (2 * n - 3 * static_cast<int64_t>(n_neighbors) - 1 <= 0 || n_neighbors + 1 > n)
     return fail(B2D_ERR_INVALID_ARG, "n_neighbors must be smaller than n / 2");
@@ -1003,7 +1224,8 @@ int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, 
   const int kk1    = n_neighbors + 1;
   B2D_CUDA(cudaMemsetAsync(penalty, 0, 8, s));
   // neighbours in the embedded space (the sample itself included, as in the reference)
-  int rc = b2d_knn_l2(stream, emb_idx, emb_dist, x_embedded, lde, x_embedded, lde, n, n, d, kk1, 0, base + L.scratch, L.knn_bytes);
+  int rc = b2d_knn(stream, emb_idx, emb_dist, knn_metric, x_embedded, lde, x_embedded, lde, n, n, d, kk1, base + L.scratch,
+                   L.knn_bytes);
   if (rc) return rc;
   for (int64_t r0 = 0; r0 < n; r0 += L.chunk) {
     const int64_t rows = std::min<int64_t>(L.chunk, n - r0);
@@ -1013,11 +1235,23 @@ int b2d_trustworthiness_score(void* stream, double* score_host, const float* x, 
     trust_rank_kernel<<<static_cast<unsigned>(rows), 256, 0, s>>>(slab, L.ld, r0, n, emb_idx, kk1, n_neighbors, penalty);
     B2D_CUDA(cudaGetLastError());
   }
-  unsigned long long t = 0;
-  B2D_CUDA(cudaMemcpyAsync(&t, penalty, 8, cudaMemcpyDeviceToHost, s));
-  B2D_CUDA(cudaStreamSynchronize(s));
-  const double nn = static_cast<double>(n), kk = static_cast<double>(n_neighbors);
-  *score_host = 1.0 - (2.0 / ((nn * kk) * ((2.0 * nn) - (3.0 * kk) - 1.0))) * static_cast<double>(t);
+  trust_finish_kernel<<<1, 1, 0, s>>>(penalty, score, n, n_neighbors);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+int b2d_row_argmin(void* stream, int32_t* out, const float* in, int64_t ld, int64_t rows, int64_t n)
+{
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows < 0 || n < 0 || ld < n) return fail(B2D_ERR_INVALID_ARG, "bad extents");
+  if (n > 0x7fffffffll) return fail(B2D_ERR_INVALID_ARG, "row length exceeds 31 bits");
+  if (rows == 0) return B2D_OK;
+  if (!out || (!in && n > 0)) return fail(B2D_ERR_INVALID_ARG, "null out / in");
+  if (n <= 2048)
+    row_argmin_kernel<true><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(out, in, ld, rows, n);
+  else
+    row_argmin_kernel<false><<<static_cast<unsigned>(rows), 256, 0, s>>>(out, in, ld, rows, n);
+  B2D_CUDA(cudaGetLastError());
   return B2D_OK;
 }
 

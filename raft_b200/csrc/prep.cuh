@@ -37,6 +37,7 @@ struct PrepSide {
   int64_t rows;
   __half* op;       // [rows][nkb][64]
   float* tvec;      // [rows]
+  float* svec;      // [rows] 2^(E - e_row): 1 for every row that shares the matrix exponent E (see prep_split_kernel)
   const float* ext_norm_sq;  // optional caller-provided squared norms (fusedL2NN xn/yn)
 };
 
@@ -51,6 +52,7 @@ struct PrepParams {
   unsigned* gmax;    // [2] float bits of the per-matrix maximum (zeroed before prep_max_kernel)
   float* coef;       // [1] the epilogue scalar c
   unsigned* has_lo;  // [1] set to 1 when any lo half is non-zero (zeroed before the kernels run)
+  unsigned* nonuni;  // [2] set to 1 when some row of x / y took its own exponent (zeroed before the kernels run)
 };
 
 template <typename T>
@@ -146,11 +148,22 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   float mean, amax;
   double ss;
   row_stats(row, sd.cs, p.k, p.center, p.xform, lane, mean, ss, amax);
-  float scale = ldexpf(1.f, which ? ey : ex);
-  if (p.mode == PREP_COSINE) {
-    const double nrm = sd.ext_norm_sq ? sqrt(static_cast<double>(sd.ext_norm_sq[r])) : sqrt(ss);
-    scale            = static_cast<float>(static_cast<double>(scale) / nrm);  // 1/0 -> inf -> NaN distances, like 0/0 in the definition
+  // One exponent E per matrix puts the matrix maximum in [2^14, 2^15).  A row whose own maximum lands more than
+  // 2^12 below that (a single outlier / sentinel element elsewhere in the matrix: ADVICE r1) would slide towards the
+  // fp16 subnormals and lose the 22 bits the split promises -- such a row takes its OWN exponent e_row, and the
+  // epilogue multiplies its products by 2^(E - e_row) (exact: a power of two).  Ordinary data never takes this
+  // branch: svec == 1 everywhere and the results are bit-identical to the single-scale scheme.
+  const int E      = which ? ey : ex;
+  const double nrm = p.mode == PREP_COSINE ? (sd.ext_norm_sq ? sqrt(static_cast<double>(sd.ext_norm_sq[r])) : sqrt(ss)) : 1.0;
+  const float aeff = p.mode == PREP_COSINE ? (nrm > 0.0 ? static_cast<float>(static_cast<double>(amax) / nrm) : 0.f) : amax;
+  int e_row        = E;
+  if (aeff > 0.f && aeff < 3.0e38f && ldexpf(aeff, E) < 8.0f) {
+    e_row = max(E, min(scale_exponent(aeff), E + 120));
+    if (lane == 0 && *reinterpret_cast<volatile unsigned*>(&p.nonuni[which]) == 0u) atomicExch(&p.nonuni[which], 1u);
   }
+  float scale = ldexpf(1.f, e_row);
+  if (p.mode == PREP_COSINE) scale = static_cast<float>(static_cast<double>(scale) / nrm);  // 1/0 -> inf -> NaN distances, like 0/0 in the definition
+  if (lane == 0) sd.svec[r] = ldexpf(1.f, E - e_row);
 
   __half* orow   = sd.op + r * static_cast<int64_t>(p.nkb) * 64;
   const int kpad = p.nkb * 32;

@@ -78,6 +78,10 @@ __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads)
 {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nthreads)
+{
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const void* tmap)
@@ -105,6 +109,25 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
     "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
     :
     : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+    : "memory");
+}
+// 1-D bulk copy shared -> global (UBLKCP), bulk async-group completion, L2 cache-policy hint.
+// Both addresses 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :
+               : "l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+// 3-D tiled store shared -> global; box elements outside the tensor are not written (also for negative coordinates)
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             uint64_t policy)
+{
+  asm volatile(
+    "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+    :
+    : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
     : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -73,6 +73,8 @@ struct ScreenParams {
   int64_t n_items;
   const float* yt;        // [n] |y_j|^2
   const float* coef;      // [1] -2 * 2^-(ex+ey)
+  const float* xsc;       // [m] per-row scale of x (prep.cuh; 1 unless the row took its own exponent)
+  const unsigned* nonuni; // [2] some row of x / y has its own exponent (y: fused_nn_keys sends everything to the exact kernel)
   float2* aux;            // [m] (U_i - |x_i|^2 rounded up, -|x_i|); the bound tightens as candidates are found
   int2* cand;             // candidate (row, column) list ...
   unsigned* cand_cnt;     // ... its fill counter ...
@@ -234,8 +236,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q   = warp & 3;        // TMEM lane quarter this warp may read: tile rows [32q, 32q+32)
     const int g   = SC_SETS == 2 ? ((w & 7) >> 2) : (w >> 2);  // column slice of the tile: [SC_CW g, SC_CW (g+1))
     const int et  = threadIdx.x - 64;
-    const float cf     = __ldg(p.coef);
-    const uint64_t cf2 = pk(cf, cf);
+    const float cf0 = __ldg(p.coef);
+    const bool xnu  = __ldg(&p.nonuni[0]) != 0u;
     const float2 aux_none = make_float2(__int_as_float(0xff800000), 0.f);  // rows beyond m: threshold NaN, never taken
     uint32_t t_it = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -284,6 +286,9 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const float2 aux_c  = aux_nxt;
         aux_nxt             = aux_none;
         if (mt_own + SC_SETS < mt1 && row + SC_SETS * TC_BM < p.m) aux_nxt = __ldg(&p.aux[row + SC_SETS * TC_BM]);
+        // thread == row: a row with its own exponent just has its own coefficient
+        const float cf     = (xnu && row < p.m) ? cf0 * __ldg(&p.xsc[row]) : cf0;
+        const uint64_t cf2 = pk(cf, cf);
         // U_i - |x_i|^2 + |x_i| * max margin, nudged up so that it stays an upper bound
         float thr = fmaf(-aux_c.y, ny_max, aux_c.x);
         thr       = thr + fabsf(thr) * (1.f / 4194304.f);

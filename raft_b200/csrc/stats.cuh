@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(256) sil_row_kernel(const float* slab, int64_t
   if (threadIdx.x == 0) {
     const int own = labels[row0 + r];
     float s = 0.f;
-    if (counts[own] > 1) {
+    if (own < 0 || own >= n_labels) {
+      s = __int_as_float(0x7fc00000);  // invalid label: NaN (see sil_finish_kernel)
+    } else if (counts[own] > 1) {
       // the sample's distance to itself is 0 by definition (the reference gets that from x == y aliasing;
       // here the column side is a permuted copy, so whatever rounding left in d(i, i) is taken out)
       const float av = (sums[own] - d[where[row0 + r]]) / static_cast<float>(counts[own] - 1);
@@ -90,9 +92,12 @@ __global__ void __launch_bounds__(256) sil_row_kernel(const float* slab, int64_t
   }
 }
 
-__global__ void sil_finish_kernel(const double* total, float* score, int64_t n)
+// labels outside [0, n_labels) were flagged by sil_count_kernel: the score is NaN then (device-side validation,
+// the call never synchronises)
+__global__ void sil_finish_kernel(const double* total, float* score, int64_t n, const unsigned* bad)
 {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *score = static_cast<float>(*total / static_cast<double>(n));
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    *score = *bad ? __int_as_float(0x7fc00000) : static_cast<float>(*total / static_cast<double>(n));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -156,6 +161,13 @@ __global__ void __launch_bounds__(256) trust_rank_kernel(const float* slab, int6
     const long long r = static_cast<long long>(cnt[threadIdx.x]) + 1;  // the sample itself comes first
     if (r > n_neighbors) atomicAdd(penalty, static_cast<unsigned long long>(r - n_neighbors));
   }
+}
+
+// score = 1 - 2 / (n k (2n - 3k - 1)) * sum of the penalties, written to DEVICE memory
+__global__ void trust_finish_kernel(const unsigned long long* penalty, double* score, int64_t n, int n_neighbors)
+{
+  const double nn = static_cast<double>(n), kk = static_cast<double>(n_neighbors);
+  *score = 1.0 - (2.0 / ((nn * kk) * ((2.0 * nn) - (3.0 * kk) - 1.0))) * static_cast<double>(*penalty);
 }
 
 }  // namespace b2d

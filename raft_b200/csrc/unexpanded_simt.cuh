@@ -24,7 +24,8 @@ constexpr int UX_TMA_STAGES = 3;
 constexpr int UX_TMA_SMEM_BYTES = UX_TMA_STAGES * (UX_BM + UX_BN) * UX_KB * 4 + 64;
 
 enum UxMetric : int { UX_L1 = 0, UX_L2 = 1, UX_L2SQRT = 2, UX_LINF = 3, UX_CANBERRA = 4, UX_LP = 5,
-                      UX_HAMMING = 6, UX_KL = 7, UX_JS = 8 };
+                      UX_HAMMING = 6, UX_KL = 7, UX_JS = 8,
+                      UX_KL_REV = 9 };  // KL with the operand roles swapped: sum b log(b/a) (Fortran-order inputs)
 
 struct UxParams {
   const float* x;
@@ -65,6 +66,11 @@ __device__ __forceinline__ void ux_acc(float& acc, float a, float b, float p)
     // see ux_fin).  log2 domain, scaled by ln 2 at the end; a zero-padded k tail adds 0.
     const float t = a * (__log2f(a) - __log2f(b));
     acc += (a == 0.f) ? 0.f : t;
+  } else if (kMetric == UX_KL_REV) {
+    // the column-major entry point computes D^T with x and y exchanged (api.cu); KL is not symmetric,
+    // so the kernel accumulates KL(b || a) there -- the reference's !is_row_major branch did the same swap
+    const float t = b * (__log2f(b) - __log2f(a));
+    acc += (b == 0.f) ? 0.f : t;
   } else if (kMetric == UX_JS) {
     // sum x log(x/m) + y log(y/m), m = (x+y)/2; 0 log 0 = 0
     const float lm = __log2f(0.5f * (a + b));
@@ -83,7 +89,7 @@ __device__ __forceinline__ float ux_fin(float acc, float inv_p)
   if (kMetric == UX_L2SQRT) return sqrtf(acc);
   if (kMetric == UX_LP) return exp2f(inv_p * __log2f(acc));
   if (kMetric == UX_HAMMING) return acc * inv_p;                          // inv_p carries 1/k
-  if (kMetric == UX_KL) return 0.5f * 0.69314718056f * acc;              // 0.5 * sum x ln(x/y)
+  if (kMetric == UX_KL || kMetric == UX_KL_REV) return 0.5f * 0.69314718056f * acc;  // 0.5 * sum x ln(x/y)
   if (kMetric == UX_JS) return sqrtf(fmaxf(0.5f * 0.69314718056f * acc, 0.f));  // sqrt(JS divergence), natural log
   return acc;
 }

@@ -87,15 +87,40 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, hi
 
 
-def fused_l2_nn_sharded(X, Y_shard, idx_offset, sqrt=True, handle=None, group=None, keys=None, head_rows=None):
+def plan_exchanges(shard_rows: int, world: int):
+    """Sub-chunks (rows) a shard is searched in, with one exchange of the packed keys after each: a small head
+    first (every rank then knows the best distance found ANYWHERE in world x head rows), growing geometrically --
+    the screened search (screen_tc.cuh) keeps far fewer candidates once its bounds are global.  Depends only on
+    (shard_rows, world): pass the SAME shard_rows on every rank (n_total // world), the last sub-chunk takes
+    whatever a rank's shard has left."""
+    if world <= 1 or shard_rows <= 0:
+        return [max(shard_rows, 0)]
+    sizes, left, step = [], shard_rows, SHARD_HEAD_ROWS
+    while left > 4 * step and len(sizes) < 3:
+        sizes.append(step)
+        left -= step
+        step *= 4
+    sizes.append(left)
+    return sizes
+
+
+def fused_l2_nn_sharded(X, Y_shard, idx_offset, sqrt=True, handle=None, group=None, keys=None, head_rows=None,
+                        n_total=None):
     """Multi-GPU fusedL2NN: every rank holds all queries X [m,k] and its own row-block Y_shard of
     the database (global row index of its first row = idx_offset).  One process per GPU;
     `group` is a torch.distributed process group (NCCL over NVLink on the GPU box).
 
     Returns (indices int32 [m] -- GLOBAL database rows, distances float32 [m]) on every rank.
-    The only collective is all_reduce(MIN) over m packed int64 keys (twice for large shards, see below): NCCL has no MINLOC, and
+    The only collective is all_reduce(MIN) over m packed int64 keys: NCCL has no MINLOC, and
     signed 64-bit MIN over (ordered distance bits << 32 | index) is exactly raft::argmin_op
-    (smaller value first, then smaller index; cpp/include/raft/core/operators.hpp:187-194)."""
+    (smaller value first, then smaller index; cpp/include/raft/core/operators.hpp:187-194).
+
+    Exchange plan (the SAME number of collectives on every rank, whatever the local shard size -- shards from
+    shard_bounds differ by a row): with n_total (rows of the whole database) the shard is searched in the
+    sub-chunks of plan_exchanges(n_total // world, world), one all_reduce after each; without it, in a head of
+    min(SHARD_HEAD_ROWS, n) rows and the rest (two all_reduces, always).  No row is visited twice: every call
+    continues behind the previous one with the reduced keys, which also serve as the search's starting bounds.
+    head_rows (tests): an explicit head size, single exchange plan [head, rest]."""
     import torch.distributed as dist
 
     own = handle is None
@@ -107,29 +132,32 @@ def fused_l2_nn_sharded(X, Y_shard, idx_offset, sqrt=True, handle=None, group=No
     n = y_cai.shape[0]
     L = _lib.lib()
     ws = handle.workspace(L.b2d_fused_l2_nn_workspace_bytes(m, n, k))
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    if head_rows is not None:
+        head = max(0, min(int(head_rows), n))
+        plan = [head, n - head] if head else [n]
+    elif not multi:
+        plan = [n]
+    elif n_total is not None:
+        plan = plan_exchanges(int(n_total) // world, world)
+    else:
+        plan = [SHARD_HEAD_ROWS, -1]          # -1: the rest (rank-invariant count: always two exchanges)
     with torch.cuda.stream(handle.torch_stream):
         if keys is None:
             keys = torch.empty(m, dtype=torch.int64, device=handle.device)
         kvp = torch.empty((m, 2), dtype=torch.int32, device=handle.device)
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-        # Two exchanges when the shard is large: the first, after a small head of every shard, gives
-        # each rank the best distance found ANYWHERE so far -- the screened search (screen_tc.cuh) then
-        # starts the rest of its shard from global bounds and keeps far fewer candidates.  No row is
-        # visited twice: the second call continues behind the head with the reduced keys.
-        if head_rows is None:
-            head = SHARD_HEAD_ROWS if (multi and n >= 4 * SHARD_HEAD_ROWS) else 0
-        else:
-            head = max(0, min(int(head_rows), n))
-        if head:
-            _lib.check(L.b2d_fused_l2_nn_keys(handle.stream_ptr, keys.data_ptr(), x_cai.data, k, y_cai.data, k,
-                                              None, None, m, head, k, int(idx_offset), 1, ws.data_ptr(), ws.numel()))
+        done = 0
+        for c, rows in enumerate(plan):
+            last = c == len(plan) - 1
+            rows = n - done if (last or rows < 0) else max(0, min(rows, n - done))
+            # (a call with 0 rows only initialises the keys; the collective below still takes place)
+            _lib.check(L.b2d_fused_l2_nn_keys(handle.stream_ptr, keys.data_ptr(), x_cai.data, k,
+                                              y_cai.data + done * k * 4, k, None, None, m, rows, k,
+                                              int(idx_offset) + done, 1 if c == 0 else 0, ws.data_ptr(), ws.numel()))
+            done += rows
             if multi:
                 dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
-        _lib.check(L.b2d_fused_l2_nn_keys(handle.stream_ptr, keys.data_ptr(), x_cai.data, k,
-                                          y_cai.data + head * k * 4, k, None, None, m, n - head, k,
-                                          int(idx_offset) + head, 0 if head else 1, ws.data_ptr(), ws.numel()))
-        if multi:
-            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
         _lib.check(L.b2d_fused_l2_nn_finalize(handle.stream_ptr, kvp.data_ptr(), keys.data_ptr(), m,
                                               1 if sqrt else 0, ws.data_ptr(), ws.numel()))
     if own:

@@ -44,6 +44,12 @@ def silhouette_score(X, labels, n_labels=None, metric="sqeuclidean_unexpanded", 
                                       ws.data_ptr(), ws.numel()))
     handle.sync()
     val = float(score.item())
+    if val != val:
+        # the C ABI validates labels on the device and poisons the score instead of synchronising; this wrapper
+        # returns a host float (it has synchronised already), so it can turn that into the reference's error
+        lt = torch.as_tensor(labels, device=handle.device)
+        if int(lt.min().item()) < 0 or int(lt.max().item()) >= int(n_labels):
+            raise _lib.LogicError("labels must lie in [0, n_labels)")
     return (val, per) if return_samples else val
 
 
@@ -54,7 +60,7 @@ def trustworthiness_score(X, X_embedded, n_neighbors=5, metric="euclidean", batc
     of max(0, r(i, j) - k), r = rank of j among the original-space neighbours of i
     (raft::stats::trustworthiness_score, cpp/include/raft/stats/trustworthiness_score.cuh:29-41; same
     definition as sklearn.manifold.trustworthiness).  ``metric``: original-space metric (any name of
-    ``pairwise_distance``); the embedded-space neighbours use Euclidean distance.  ``batch_size``: rows of
+    ``pairwise_distance`` from the L2 / cosine families); the embedded-space neighbours use the same metric, as in the reference.  ``batch_size``: rows of
     the original-space distance matrix alive at a time (0: about 1 GiB).  Returns a float."""
     import ctypes
     x_cai, e_cai = cai_wrapper(X), cai_wrapper(X_embedded)
@@ -72,7 +78,9 @@ def trustworthiness_score(X, X_embedded, n_neighbors=5, metric="euclidean", batc
     if need == 2 ** 64 - 1:
         raise _lib.LogicError("n_neighbors must be in [1, 63] and the metric one of pairwise_distance's")
     ws = handle.workspace(need)
-    out = ctypes.c_double(0.0)
-    _lib.check(L.b2d_trustworthiness_score(handle.stream_ptr, ctypes.byref(out), x_cai.data, m, e_cai.data, d, n, m, d,
+    with torch.cuda.stream(handle.torch_stream):
+        out = torch.empty(1, dtype=torch.float64, device=handle.device)   # the C ABI writes device memory, never syncs
+    _lib.check(L.b2d_trustworthiness_score(handle.stream_ptr, out.data_ptr(), x_cai.data, m, e_cai.data, d, n, m, d,
                                            int(n_neighbors), mt, int(batch_size), ws.data_ptr(), ws.numel()))
-    return float(out.value)
+    handle.sync()
+    return float(out.item())

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include <raft/distance/fused_l2_nn.cuh>
+#include <raft/matrix/argmin.cuh>
 #include <raft/neighbors/brute_force.cuh>
 #include <raft/stats/silhouette_score.cuh>
 #include <raft/stats/trustworthiness_score.cuh>
@@ -27,7 +28,14 @@ int main()
   cudaStreamCreate(&s);
   int bad = 0;
   {
+#ifdef RAFT_B200_USE_REAL_RAFT
+    // boundary compile test: raft::resources of tests/cpp/mock_raft has the reference's surface only (no
+    // workspace(), no stream()); temporaries must come from raft::resource::get_workspace_resource_ref
+    raft::resources handle;
+    handle.mock_set_stream(s);
+#else
     raft::resources handle(s);
+#endif
     // legacy pointer API, as stats/detail/silhouette_score.cuh:205-206 calls it
     raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::L2Unexpanded);
     std::vector<float> h1(m * n), h2(m * n);
@@ -73,6 +81,47 @@ int main()
         if (c < bv) { bv = c; best = j; }
       }
       if (hc[i].key != best || std::fabs(hc[i].value - bv) > 1e-4 * std::fmax(std::fabs(bv), 1e-2)) ++bad;
+    }
+    // generic fusedL2NN<..., ReduceOpT, KVPReduceOpT>: OutT = KeyValuePair (MinAndDistanceReduceOp) and OutT = float
+    // (MinReduceOp), plus initOutBuffer = false folding into what the caller already holds
+    {
+      using KVP = raft::KeyValuePair<int, float>;
+      raft::distance::fusedL2NN<float, KVP, int>(nn, x, y, (const float*)nullptr, (const float*)nullptr, m, n, k, nullptr,
+                                                 raft::distance::MinAndDistanceReduceOp<int, float>{},
+                                                 raft::distance::KVPMinReduce<int, float>{}, false, true, s);
+      std::vector<KVP> hg(m);
+      cudaMemcpyAsync(hg.data(), nn, m * sizeof(KVP), cudaMemcpyDeviceToHost, s);
+      float* dmin; cudaMalloc(&dmin, m * 4);
+      std::vector<float> pre(m, 1e30f);
+      pre[7] = -1.f;   // smaller than any distance: must survive initOutBuffer = false
+      cudaMemcpyAsync(dmin, pre.data(), m * 4, cudaMemcpyHostToDevice, s);
+      raft::distance::fusedL2NN<float, float, int>(dmin, x, y, (const float*)nullptr, (const float*)nullptr, m, n, k, nullptr,
+                                                   raft::distance::MinReduceOp<int, float>{},
+                                                   raft::distance::KVPMinReduce<int, float>{}, false, false, s);
+      std::vector<float> hm(m);
+      cudaMemcpyAsync(hm.data(), dmin, m * 4, cudaMemcpyDeviceToHost, s);
+      raft::resource::sync_stream(handle);
+      for (int i = 0; i < m; ++i) {
+        if (hg[i].key != hn[i].key || hg[i].value != hn[i].value) ++bad;
+        if (i == 7 ? hm[i] != -1.f : hm[i] != hn[i].value) ++bad;
+      }
+      cudaFree(dmin);
+    }
+    // raft::matrix::argmin over the materialised matrix == the fused arg-min (the separate-pass form)
+    {
+      auto xv = raft::make_device_matrix_view<const float, int>(x, m, k);
+      auto yv = raft::make_device_matrix_view<const float, int>(y, n, k);
+      auto dv = raft::make_device_matrix_view<float, int>(d, m, n);
+      raft::distance::pairwise_distance(handle, xv, yv, dv, raft::distance::DistanceType::L2Expanded);
+      int* am; cudaMalloc(&am, m * 4);
+      raft::matrix::argmin<float, int, int>(handle, raft::make_device_matrix_view<const float, int>(d, m, n), am, m);
+      std::vector<int> ha(m);
+      cudaMemcpyAsync(ha.data(), am, m * 4, cudaMemcpyDeviceToHost, s);
+      raft::resource::sync_stream(handle);
+      int diff = 0;
+      for (int i = 0; i < m; ++i) diff += ha[i] != hn[i].key;
+      if (diff > 1) ++bad;   // (a near-tie may resolve differently between the tensor-path matrix and the fused search)
+      cudaFree(am);
     }
     // brute_force::knn (k = 3): first neighbour == the fused arg-min, distances ascending
     {
@@ -120,12 +169,37 @@ int main()
         handle, x, x, m, k, k, 5, 128);
       if (tw != 1.0) { std::printf("trustworthiness %f\n", tw); ++bad; }
     }
+    // strided (padded leading dimension) mdspan views: same numbers as the dense call
+    {
+      const int ldx = k + 4, ldd = n + 8;
+      float *xp, *dp;
+      cudaMalloc(&xp, (size_t)m * ldx * 4); cudaMalloc(&dp, (size_t)m * ldd * 4);
+      cudaMemcpy2D(xp, ldx * 4, x, k * 4, k * 4, m, cudaMemcpyDeviceToDevice);
+      auto xs = raft::make_device_strided_matrix_view<const float, int>(xp, m, k, ldx);
+      auto ys = raft::make_device_strided_matrix_view<const float, int>(y, n, k, k);
+      auto ds = raft::make_device_strided_matrix_view<float, int>(dp, m, n, ldd);
+      raft::distance::pairwise_distance(handle, xs, ys, ds, raft::distance::DistanceType::L2Expanded);
+      auto xv = raft::make_device_matrix_view<const float, int>(x, m, k);
+      auto yv = raft::make_device_matrix_view<const float, int>(y, n, k);
+      auto dv = raft::make_device_matrix_view<float, int>(d, m, n);
+      raft::distance::pairwise_distance(handle, xv, yv, dv, raft::distance::DistanceType::L2Expanded);
+      std::vector<float> a((size_t)m * n), b((size_t)m * n);
+      cudaMemcpy2DAsync(a.data(), n * 4, dp, ldd * 4, n * 4, m, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(b.data(), d, (size_t)m * n * 4, cudaMemcpyDeviceToHost, s);
+      raft::resource::sync_stream(handle);
+      for (size_t i = 0; i < a.size(); ++i)
+        if (a[i] != b[i]) { ++bad; break; }
+      cudaFree(xp); cudaFree(dp);
+    }
     // error convention: unsupported metric -> raft::logic_error
     bool threw = false;
     try { raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::JaccardExpanded); }
     catch (raft::logic_error const&) { threw = true; }
     if (!threw) ++bad;
   }
+#ifdef RAFT_B200_USE_REAL_RAFT
+  if (rmm::device_async_resource_ref::live() == 0) { std::printf("no scratch came from the workspace resource\n"); ++bad; }
+#endif
   std::printf(bad ? "FAIL %d\n" : "PASS\n", bad);
   return bad ? 1 : 0;
 }

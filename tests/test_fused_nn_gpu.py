@@ -313,3 +313,22 @@ def test_screened_cosine_family_nn(metric, shape, kind):
         assert abs(d[i, gi[i]] - rv[i]) <= 2e-5 * max(rv[i], 1e-3)
     # 1 - cos of near-parallel vectors: absolute floor of a few fp32 ulp of 1
     assert np.all(np.abs(gv - rv) <= 1e-4 * np.abs(rv) + 4e-7)
+
+
+@pytest.mark.parametrize("n", [3000, 70000])
+def test_fused_l2_nn_with_outlier_rows(n):
+    """Sentinel rows (1e9) in the queries and in the database: ordinary rows must still find their exact nearest
+    neighbour (per-row exponents, prep.cuh); with n = 70000 the screened search sees rows of y with their own
+    exponent and must hand over to the exact kernel."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1500, 96)).astype(np.float32)
+    y = rng.standard_normal((n, 96)).astype(np.float32)
+    x[3] *= 1.0e9
+    y[n // 2] *= 1.0e9
+    y[7] *= 2.0e8
+    ri, rv = oracle.fused_l2_nn(x, y, sqrt=False)
+    gi, gv = fused_l2_nn(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sqrt=False)
+    gi, gv = gi.cpu().numpy(), gv.cpu().numpy()
+    tie_aware_index_check(gi, ri, x, y)
+    ok, msg = oracle.match_approx(gv, rv, 1e-4)
+    assert ok, msg

@@ -139,3 +139,24 @@ def test_pylibraft_alias_namespace():
     assert d.pairwise_distance is r.pairwise_distance and d.fused_l2_nn_argmin is r.fused_l2_nn_argmin
     assert "euclidean" in d.DISTANCE_TYPES and callable(pylibraft.config.set_output_as)
     assert pylibraft.common.DeviceResources is not None
+
+
+def test_exchange_plan_is_rank_invariant_and_covers_every_shard():
+    """ranks whose shards differ by one row must issue the SAME number of all_reduces.  The
+    plan depends on (n_total // world, world) only; a rank's last sub-chunk takes what its shard has left."""
+    from raft_b200.distance import shard_bounds
+    from raft_b200.distance.fused_l2_nn import SHARD_HEAD_ROWS, plan_exchanges
+    for n_total, world in [(8_000_000, 8), (8_000_001, 8), (1_048_577, 8), (4 * SHARD_HEAD_ROWS * 8 + 3, 8),
+                           (4 * SHARD_HEAD_ROWS * 2 - 1, 2), (1000, 4), (5, 8), (8_000_000, 2), (8_000_000, 1)]:
+        plan = plan_exchanges(n_total // world, world)
+        assert all(p >= 0 for p in plan) and sum(plan) == n_total // world
+        assert len(plan) <= 4
+        for r in range(world):
+            lo, hi = shard_bounds(n_total, world, r)
+            n_local, done = hi - lo, 0
+            for c, rows in enumerate(plan):          # the loop of fused_l2_nn_sharded
+                rows = n_local - done if c == len(plan) - 1 else max(0, min(rows, n_local - done))
+                assert rows >= 0
+                done += rows
+            assert done == n_local
+    assert plan_exchanges(1_000_000, 8)[0] == SHARD_HEAD_ROWS and len(plan_exchanges(1_000_000, 8)) >= 2

@@ -197,6 +197,22 @@ def test_fortran_order(metric):
     check(got, oracle.pairwise_distance(x, y, metric))
 
 
+def test_fortran_order_kl_divergence_is_not_transposed():
+    # KLDivergence is the one asymmetric metric: the column-major entry computes D^T with the operands
+    # exchanged, so the kernel must swap their roles back (the reference's op had an explicit
+    # !is_row_major branch)
+    rng = np.random.default_rng(11)
+    a = rng.random((90, 37)); b = rng.random((70, 37))
+    a /= a.sum(1, keepdims=True); b /= b.sum(1, keepdims=True)
+    a, b = a.astype(np.float32), b.astype(np.float32)
+    af = torch.from_numpy(a).cuda().t().contiguous().t()
+    bf = torch.from_numpy(b).cuda().t().contiguous().t()
+    got = pairwise_distance(af, bf, metric=DT.KLDivergence).copy_to_host()
+    ref = oracle.pairwise_distance(a, b, DT.KLDivergence)
+    check(got, ref)
+    assert not oracle.match_approx(got, oracle.pairwise_distance(b, a, DT.KLDivergence).T, EPS)[0]
+
+
 def test_fp16_inputs_tolerance_study():
     """BASELINE.json configs[4] (fp16 in / fp32 accumulate): exact w.r.t. the fp16-rounded inputs,
     ~1e-3 w.r.t. the original fp32 inputs."""
@@ -281,3 +297,27 @@ def test_full_size_sampled_check():
     # every row block / column block was written (no stale tile): min over each 128x256 tile > 0
     assert torch.isfinite(out).all()
     assert (out.view(-1)[:: 104729] >= 0).all()
+
+
+@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.L2SqrtExpanded, DT.InnerProduct])
+@pytest.mark.parametrize("where", ["x", "y", "both"])
+def test_outlier_rows_do_not_degrade_ordinary_rows(metric, where):
+    """one sentinel row ~1e9 in O(1) data used to push every ordinary row into the fp16
+    subnormals (single power-of-two scale per matrix).  Rows far below the matrix maximum now take their own
+    exponent (prep.cuh), so the ordinary pairs keep the 1e-4 bar; pairs that involve the sentinel are exact to
+    fp32 rounding of their own (huge) magnitude."""
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((300, 72)).astype(np.float32)
+    y = rng.standard_normal((520, 72)).astype(np.float32)
+    if where in ("x", "both"):
+        x[17] = 1.0e9 * rng.standard_normal(72).astype(np.float32)
+    if where in ("y", "both"):
+        y[333] = 3.0e8 * rng.standard_normal(72).astype(np.float32)
+        y[5, 11] = -7.0e7                                    # a single huge element inside an ordinary row
+    got = run(x, y, metric).astype(np.float64)
+    ref = oracle.pairwise_distance(x, y, metric)
+    if metric == DT.InnerProduct:
+        scale = np.sqrt(oracle.row_norm_sq(x))[:, None] * np.sqrt(oracle.row_norm_sq(y))[None, :]
+        assert (np.abs(got - ref) <= 2e-5 * scale + 1e-6).all()
+    else:
+        check(got, ref)
