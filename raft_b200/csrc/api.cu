@@ -13,6 +13,7 @@
 
 #include "../../include/raft_b200.h"
 #include "expanded_tc.cuh"
+#include "expanded_tc2.cuh"
 #include "screen_tc.cuh"
 #include "prep.cuh"
 #include "unexpanded_simt.cuh"
@@ -220,11 +221,7 @@ static int make_dist_map3(CUtensorMap* map, const float* base, int64_t m, int64_
   const cuuint64_t inner = cols >= 128 ? 128 : static_cast<cuuint64_t>(cols);
   cuuint64_t dims[3]    = {inner, static_cast<cuuint64_t>(cols >= 128 ? cols / 128 : 1), static_cast<cuuint64_t>(m)};
   cuuint64_t strides[2] = {512, static_cast<cuuint64_t>(ldd) * 4};
-#if B2D_STG_MODE == 8
-  cuuint32_t box[3]     = {132, 2, 4};
-#else
   cuuint32_t box[3]     = {132, 2, 8};
-#endif
   cuuint32_t estr[3]    = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base + first_col), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -252,6 +249,49 @@ static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensor
   if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, kTma>(s, ma, mb, md, mr, p, grid);
   if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, kTma>(s, ma, mb, md, mr, p, grid);
   return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, kTma>(s, ma, mb, md, mr, p, grid);
+}
+
+static std::atomic<int> g_pair_kernel{0};  // b2d_set_option("pairwise_2cta", 1): the CTA-pair kernel (expanded_tc2.cuh) for k <= 128
+
+// K1, 2-CTA form (expanded_tc2.cuh): EPI_STORE, k <= 128, aligned output
+template <int kPost>
+static int launch_tc2_inst(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                           const TcParams& p, int grid)
+{
+  B2D_CUDA(cudaFuncSetAttribute(expanded_tc2_kernel<kPost>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(T2_SMEM_BYTES)));
+  expanded_tc2_kernel<kPost><<<grid, T2_THREADS, T2_SMEM_BYTES, s>>>(ma, mb, md, p);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+static int launch_tc2(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int post, int sms)
+{
+  p.nkb     = static_cast<int>((k + 31) / 32);
+  p.tiles_m = static_cast<int>((p.m + TC_BM - 1) / TC_BM);
+  p.tiles_n = static_cast<int>((p.n + TC_BN - 1) / TC_BN);
+  const int clusters  = std::max(1, sms / 2);
+  const int pairs_m   = (p.tiles_m + 1) / 2;
+  const int64_t total = static_cast<int64_t>(pairs_m) * p.tiles_n;
+  int64_t chunk       = total / (static_cast<int64_t>(clusters) * 6);
+  chunk               = std::max<int64_t>(1, std::min<int64_t>(chunk, 16));
+  chunk               = std::min<int64_t>(chunk, pairs_m);
+  p.chunk    = static_cast<int>(chunk);        // PAIRS of x tiles per work item
+  p.chunks_m = (pairs_m + p.chunk - 1) / p.chunk;
+  p.n_items  = static_cast<int64_t>(p.tiles_n) * p.chunks_m;
+  p.xt = w.xt; p.yt = w.yt; p.coef = w.coef; p.has_lo = w.has_lo; p.xsc = w.xsc; p.ysc = w.ysc; p.nonuni = w.nonuni;
+  if (p.n_items == 0) return B2D_OK;
+  CUtensorMap ma, mb, md;
+  memset(&md, 0, sizeof(md));
+  int rc = make_operand_map(&ma, w.xop, p.m, p.nkb, TC_BM);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, w.yop, p.n, p.nkb, 128);   // each CTA of a pair loads ITS 128 rows of the y block
+  if (rc) return rc;
+  if (p.n >= 128) { rc = make_dist_map3(&md, p.dist, p.m, 0, p.n / 128 * 128, p.ldd); if (rc) return rc; }
+  const int grid = 2 * static_cast<int>(std::min<int64_t>(p.n_items, clusters));
+  if (post == POST_NONE) return launch_tc2_inst<POST_NONE>(s, ma, mb, md, p, grid);
+  if (post == POST_CLAMP) return launch_tc2_inst<POST_CLAMP>(s, ma, mb, md, p, grid);
+  return launch_tc2_inst<POST_CLAMP_SQRT>(s, ma, mb, md, p, grid);
 }
 
 static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k, int epi, int post, int kb0 = 0,
@@ -304,7 +344,9 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   // register->global path
   bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0) &&
              p.acc_mode == 0;  // the K-chunked read-modify-write epilogue lives in the direct path
-#if B2D_STG_MODE == 0 || B2D_STG_MODE == 7 || B2D_STG_MODE == 8
+  // k <= 128 with an aligned output: the CTA-pair kernel (full-width output rows, expanded_tc2.cuh)
+  if (tma && resident && p.sel_s <= 1 && p.run_flag == nullptr && sms >= 2 && g_pair_kernel.load(std::memory_order_relaxed))
+    return launch_tc2(s, w, p, k, post, sms);
   if (tma) {
     // dist [m][n] fp32 (row pitch ldd), box = 32 x 32, SWIZZLE_128B (inner box = 128 bytes); edge clipping works in
     // 16-byte units, hence n % 4 == 0 above
@@ -318,18 +360,8 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B2D_ERR_CUDA, "cuTensorMapEncodeTiled(dist) failed: " + std::to_string((int)r));
     mr = md;
-#if B2D_STG_MODE == 7 || B2D_STG_MODE == 8
+    // k <= 64: the full-width store path of the same kernel (3-D box {132, 2, 8} over the 128-column chunks)
     if (p.n >= 128) { rc = make_dist_map3(&mr, p.dist, p.m, 0, p.n / 128 * 128, p.ldd); if (rc) return rc; }
-#endif
-    return resident ? launch_tc_store<true, true>(s, ma, mb, md, mr, p, grid, post)
-                    : launch_tc_store<false, true>(s, ma, mb, md, mr, p, grid, post);
-  }
-#endif
-  if (tma) {
-    const int64_t full = p.n / 128 * 128;
-    if (full > 0) { rc = make_dist_map3(&md, p.dist, p.m, 0, full, p.ldd); if (rc) return rc; }
-    if (p.n > full) { rc = make_dist_map3(&mr, p.dist, p.m, full, p.n - full, p.ldd); if (rc) return rc; }
-    if (full == 0) md = mr;  // (never addressed inside the matrix: every box of the main map is out of range)
     return resident ? launch_tc_store<true, true>(s, ma, mb, md, mr, p, grid, post)
                     : launch_tc_store<false, true>(s, ma, mb, md, mr, p, grid, post);
   }
@@ -550,8 +582,10 @@ int b2d_set_option(const char* name, double value)
     g_nn_tau.store(static_cast<float>(value));
   } else if (n == "nn_screen") {
     g_nn_screen.store(value != 0.0 ? 1 : 0);
+  } else if (n == "pairwise_2cta") {
+    g_pair_kernel.store(value != 0.0 ? 1 : 0);
   } else {
-    return fail(B2D_ERR_INVALID_ARG, "unknown option '" + n + "' (nn_tau, nn_screen)");
+    return fail(B2D_ERR_INVALID_ARG, "unknown option '" + n + "' (nn_tau, nn_screen, pairwise_2cta)");
   }
   return B2D_OK;
 }

@@ -106,25 +106,8 @@ struct TcParams {
 
 constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES_RES * TC_A_BYTES;  // 224 KB
 static_assert((size_t)TC_STAGES_STR * (TC_A_BYTES + TC_B_BYTES) <= TC_SMEM_OPERANDS, "streaming carve fits");
-#ifndef B2D_STG_MODE
-#define B2D_STG_MODE 0   // 0: TMA tensor stores of swizzled 32x32 blocks (shipped); 1-6: store-path experiments, see DESIGN.md
-#endif
-constexpr int TC_STG_WROW     = 512 + 32;   // mode 5: warp-private staged half row (128 fp32) + 32 B (rows of a half-warp on disjoint banks)
-constexpr int TC_STG_WBUF     = 7 * TC_STG_WROW + 512;  // 8 rows, the last one unpadded
-constexpr int TC_STG_ROW      = 1024 + 32;  // staged tile row: 256 fp32 + 32 B of padding (4 rows of a half-warp's 8-byte stores on disjoint banks)
-#if B2D_STG_MODE == 0 || B2D_STG_MODE == 7
-constexpr int TC_STG_EXTRA    = 0;
+constexpr int TC_STG_ROW      = 1024 + 32;  // k <= 64 store path: staged tile row = 2 chunks x (128 + 4) floats
 constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_BN * 4 + 256;
-#elif B2D_STG_MODE == 8
-constexpr int TC_STG_EXTRA    = 8 * 4 * (1024 + 32) - 32768;  // 8 private buffers of 4 padded rows
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_STG_EXTRA + TC_BN * 4 + 256;
-#elif B2D_STG_MODE == 5
-constexpr int TC_STG_EXTRA    = 8 * TC_STG_WBUF - 32768;
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_STG_EXTRA + TC_BN * 4 + 200;
-#else
-constexpr int TC_STG_EXTRA    = 4 * 8 * TC_STG_ROW - 32768;  // the padding spills past the 32 KB carved out of the ring
-constexpr size_t TC_SMEM_BYTES = TC_SMEM_OPERANDS + TC_STG_EXTRA + TC_BN * 4 + 256;
-#endif
 static_assert(TC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
 
 // index of the s-th selected y block (see TcParams::sel_s)
@@ -207,8 +190,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* b_base = smem;  // resident slabs, or per-stage B
   uint8_t* a_base = smem + (kResident ? TC_MAX_RES_KB * TC_B_BYTES : TC_STAGES_STR * TC_B_BYTES);
-  uint8_t* stg    = smem + TC_SMEM_OPERANDS - 32768;  // kTma only: 4 pair buffers of 8 rows x TC_STG_ROW bytes
-  float* col_tb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS + TC_STG_EXTRA);  // [256] t_y of this y block
+  uint8_t* stg    = smem + TC_SMEM_OPERANDS - 32768;  // kTma only: 8 x 4 KB of store staging (one 32x32 block per epilogue warp)
+  float* col_tb   = reinterpret_cast<float*>(smem + TC_SMEM_OPERANDS);  // [256] t_y of this y block
   uint64_t* bars  = reinterpret_cast<uint64_t*>(col_tb + TC_BN);
   uint64_t* afull = bars;                       // [TC_MAX_STAGES]
   uint64_t* aempty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
@@ -391,98 +374,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool cols_in = col0 + 127 < p.n;
 
       for (int mt = mt0; mt < mt1; ++mt, ++t_it) {
-#if B2D_STG_MODE == 8
-        // ---- E4: warp (q, h = g) owns tile rows 32q + 16h + [0,16) over ALL 256 columns.  Its private staging buffer is
-        // the smem image of a 3-D TMA box {132, 2, 4}: 4 full-width rows, padded (row pitch 1056 B, chunk pitch 528 B: the
-        // pad floats lie outside dimension 0 of the tensor map), so the fragment stores are conflict-free and ONE tensor
-        // store moves 4 rows x 1 KB -- the wide-row pattern of scripts/probes/store_width.cu (22 B/clk/SM; 32x32 boxes:
-        // 19.5).  Rows 0-3 of a 16x256b fragment live in lanes 0-15, rows 4-7 in lanes 16-31: two steps per 8 rows.
-        if (kTma && kResident && static_cast<int64_t>(n_blk + 1) * TC_BN <= p.n) {
-          uint8_t* wbuf         = stg + ((warp - 2) & 7) * (4 * TC_STG_ROW);
-          const uint32_t tb_idx = t_it & 1, tph = (t_it >> 1) & 1;
-          const int64_t rbase   = static_cast<int64_t>(mt) * TC_BM + q * 32 + 16 * g;   // first of this warp's 16 rows
-          uint64_t ta2[2], cfr2[2];
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const int64_t gi = rbase + 8 * rr + quad;
-            float rv = 0.f, cr = cf;
-            if (gi < p.m) {
-              rv = __ldg(&p.xt[gi]);
-              if (xnu) cr *= __ldg(&p.xsc[gi]);
-            }
-            ta2[rr]  = pk(rv, rv);
-            cfr2[rr] = pk(cr, cr);
-          }
-          ptx::mbar_wait(&tfull[tb_idx], tph);
-          ptx::tc_fence_after();
-          const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32 + 16 * g) << 16) + (t_it & 1) * TC_BN;
-#pragma unroll 1
-          for (int rr = 0; rr < 2; ++rr) {
-            const int64_t gi = rbase + 8 * rr + quad;
-            float v[64];  // this thread's row (rr part), columns 128 cp + 8 i + 2 tq + {0,1}: v[32 cp + 2 i + {0,1}]
-#pragma unroll
-            for (int cp = 0; cp < 2; ++cp) {
-              uint32_t r0[32], r1[32];
-              ptx::tmem_ld_16x256_x8(t_base + 128 * cp, r0);
-              ptx::tmem_ld_16x256_x8(t_base + 128 * cp + 64, r1);
-              ptx::tmem_ld_wait();
-              if (rr == 1 && cp == 1) {  // last read of the accumulator: hand it back
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty[tb_idx]);
-              }
-              const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + 128 * cp + 2 * tq;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint32_t* R = i < 8 ? r0 : r1;
-                const int ii      = i & 7;
-                const float2 tb   = *reinterpret_cast<const float2*>(&col_tb[128 * cp + 8 * i + 2 * tq]);
-                uint64_t a        = rr == 0 ? pk(R[4 * ii], R[4 * ii + 1]) : pk(R[4 * ii + 2], R[4 * ii + 3]);
-                if (ynu) {
-                  const int64_t gc = gj + 8 * i;
-                  a = mul2(a, pk(__ldg(&p.ysc[gc]), __ldg(&p.ysc[gc + 1])));
-                }
-                unpk(fma2(a, cfr2[rr], add2(ta2[rr], pk(tb.x, tb.y))), v[32 * cp + 2 * i], v[32 * cp + 2 * i + 1]);
-              }
-              if (kPost != POST_NONE) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[32 * cp + c] = fmaxf(v[32 * cp + c], 0.f);
-                if (p.diag_zero && gi >= gj && gi < gj + 128) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    if (gi == gj + 8 * i) v[32 * cp + 2 * i] = 0.f;
-                    if (gi == gj + 8 * i + 1) v[32 * cp + 2 * i + 1] = 0.f;
-                  }
-                }
-                if (kPost == POST_CLAMP_SQRT) {
-#pragma unroll
-                  for (int c = 0; c < 32; ++c) asm("sqrt.approx.f32 %0, %1;" : "=f"(v[32 * cp + c]) : "f"(v[32 * cp + c]));
-                }
-              }
-            }
-#pragma unroll 1
-            for (int hs = 0; hs < 2; ++hs) {
-              if (lane == 0) ptx::tma_store_wait_read();  // the previous store out of this buffer has left it
-              __syncwarp();
-              if ((quad >> 2) == hs) {
-                uint8_t* rowp = wbuf + (quad & 3) * TC_STG_ROW + 8 * tq;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  *reinterpret_cast<float2*>(rowp + (i >> 4) * 528 + 32 * (i & 15)) = make_float2(v[2 * i], v[2 * i + 1]);
-              }
-              ptx::fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                ptx::tma_store_3d(&tmap_r, wbuf, 0, 2 * n_blk, static_cast<int32_t>(rbase + 8 * rr + 4 * hs), pol_st);
-                ptx::tma_store_commit();
-              }
-            }
-          }
-          continue;
-        }
-#endif
-#if B2D_STG_MODE == 7
-        // ---- E8 (prototype of the store path a 2-CTA kernel would use; here only where shared memory is free: k <= 64) ----
+        // ---- k <= 64: full-width store path (the resident y block leaves 64 KB of shared memory free) ----
         // warp (q, h = g) owns tile rows 32q + 16h + [0,16) over ALL 256 columns: a private buffer of 8 full-width rows
         // in the smem image of a 3-D TMA box {132, 2, 8} (padded rows: conflict-free fragment stores), ONE tensor store
         // per 8 rows x 1 KB -- the widest-row pattern of scripts/probes/store_width.cu (22 B/clk/SM vs 19.5 for 32x32 boxes)
@@ -566,8 +458,6 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
           continue;
         }
-#endif
-#if B2D_STG_MODE == 0 || B2D_STG_MODE == 7 || B2D_STG_MODE == 8
         if (kTma) {
           // ---------------- EPI_STORE through shared memory + TMA tensor store ----------------
           uint32_t tb_idx, tph;
@@ -660,214 +550,6 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
           continue;
         }
-#else
-        // (mode 6: a y block that is cut by the right edge of the matrix takes the direct register->global path below)
-        if (kTma && (B2D_STG_MODE != 6 || static_cast<int64_t>(n_blk + 1) * TC_BN <= p.n)) {
-          // ---------------- EPI_STORE through shared memory + 1-D bulk stores of whole tile rows ----------------
-          // Measured (scripts/probes/store_width.cu, store-only, 1965 MHz): what bounds this output pattern is
-          // the width of the contiguous row segment per store request, per SM clock -- 32x32 TMA boxes (128-byte
-          // row pieces, the r01 epilogue) 19.5 B/clk/SM, 4 rows x 1 KB boxes 22, and 8 rows x (4 x 256 B) bulk
-          // copies issued by one warp instruction 23.9 (a linear memset: 25.4).  So the two warps of a TMEM lane
-          // quarter (column halves g = 0, 1) share one staging buffer of 8 full-width tile rows (8 x 1 KB, rows
-          // padded by 16 B: conflict-free 8-byte stores from the 16x256b fragments) and warp g = 0 sends it off
-          // as 32 row segments of 256 B, one per lane.
-          uint32_t tb_idx, tph;
-          if (kResident) { tb_idx = t_it & 1; tph = (t_it >> 1) & 1; }
-          else { tb_idx = g; tph = t_it & 1; }
-          const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;  // rows row0 + 8j, j = 2 rh + rr
-          uint64_t ta2[4], cfr2[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float rv = 0.f, cr = cf;
-            if (row0 + 8 * j < p.m) {
-              rv = __ldg(&p.xt[row0 + 8 * j]);
-              if (xnu) cr *= __ldg(&p.xsc[row0 + 8 * j]);
-            }
-            ta2[j]  = pk(rv, rv);
-            cfr2[j] = pk(cr, cr);
-          }
-          uint8_t* pbuf           = stg + q * (8 * TC_STG_ROW);
-          const uint32_t bar_free = 2 + 2 * q, bar_full = 3 + 2 * q;
-          ptx::mbar_wait(&tfull[tb_idx], tph);
-          ptx::tc_fence_after();
-          const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                  (kResident ? (t_it & 1) * TC_BN + g * 128 : g * 256);
-#pragma unroll 1
-          for (int rh = 0; rh < 2; ++rh) {
-            uint32_t r0[32], r1[32];
-            const uint32_t t_rh = t_base + (static_cast<uint32_t>(rh * 16) << 16);
-            ptx::tmem_ld_16x256_x8(t_rh, r0);
-            ptx::tmem_ld_16x256_x8(t_rh + 64, r1);
-            if (add_cross) {  // streaming layout: the cross terms sit in their own accumulator
-              uint32_t rc[32];
-              ptx::tmem_ld_16x256_x8(t_rh + 128, rc);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; c += 2) {
-                float a, b;
-                unpk(add2(pk(r0[c], r0[c + 1]), pk(rc[c], rc[c + 1])), a, b);
-                r0[c] = __float_as_uint(a); r0[c + 1] = __float_as_uint(b);
-              }
-              ptx::tmem_ld_16x256_x8(t_rh + 128 + 64, rc);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; c += 2) {
-                float a, b;
-                unpk(add2(pk(r1[c], r1[c + 1]), pk(rc[c], rc[c + 1])), a, b);
-                r1[c] = __float_as_uint(a); r1[c + 1] = __float_as_uint(b);
-              }
-            } else {
-              ptx::tmem_ld_wait();
-            }
-            if (rh == 1) {  // everything this warp needs from the accumulator is in registers: hand it back
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&tempty[tb_idx]);
-            }
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const int j      = 2 * rh + rr;
-              const int64_t gi = row0 + 8 * j;                                          // this thread's global row
-              const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + g * 128 + 2 * tq;  // its first global column
-              float v[32];  // v[2i], v[2i+1]: columns 8i + 2tq + {0,1} of chunk 0 (i < 8) / chunk 1 (i >= 8)
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint32_t* R = i < 8 ? r0 : r1;
-                const int ii      = i & 7;
-                const float2 tb   = *reinterpret_cast<const float2*>(&col_tb[g * 128 + 8 * i + 2 * tq]);
-                uint64_t a        = pk(R[4 * ii + 2 * rr], R[4 * ii + 2 * rr + 1]);
-                if (ynu) {
-                  const int64_t gc = gj + 8 * i;
-                  a = mul2(a, pk(gc < p.n ? __ldg(&p.ysc[gc]) : 1.f, gc + 1 < p.n ? __ldg(&p.ysc[gc + 1]) : 1.f));
-                }
-                unpk(fma2(a, cfr2[j], add2(ta2[j], pk(tb.x, tb.y))), v[2 * i], v[2 * i + 1]);
-              }
-              if (kPost != POST_NONE) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
-                if (p.diag_zero && gi >= gj && gi < gj + 128) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    if (gi == gj + 8 * i) v[2 * i] = 0.f;
-                    if (gi == gj + 8 * i + 1) v[2 * i + 1] = 0.f;
-                  }
-                }
-                if (kPost == POST_CLAMP_SQRT) {
-#pragma unroll
-                  for (int c = 0; c < 32; ++c) asm("sqrt.approx.f32 %0, %1;" : "=f"(v[c]) : "f"(v[c]));
-                }
-              }
-#if B2D_STG_MODE == 5
-              // warp-private staging (8 rows x 512 B, rows padded to 528 B: conflict-free 8-byte stores from the
-              // fragments), then the LSU writes it out one row x 512 contiguous bytes per instruction
-              {
-                uint8_t* wbuf = stg + ((warp - 2) & 7) * TC_STG_WBUF;
-                uint8_t* rowp = wbuf + quad * TC_STG_WROW + 8 * tq;
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(rowp + 32 * i) = make_float2(v[2 * i], v[2 * i + 1]);
-                __syncwarp();
-                const int64_t orow0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + 8 * j;
-                const int64_t ocol  = static_cast<int64_t>(n_blk) * TC_BN + g * 128 + 4 * lane;
-                float* gp           = p.dist + orow0 * p.ldd + ocol;
-                const bool col_ok   = ocol < p.n;  // n % 4 == 0: a float4 is inside or outside as a whole
-#pragma unroll
-                for (int r8 = 0; r8 < 8; ++r8) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(wbuf + r8 * TC_STG_WROW + 16 * lane);
-                  if (col_ok && orow0 + r8 < p.m) ptx::st_global_cs_v4(gp + r8 * p.ldd, w4);
-                }
-              }
-#else
-              // the pair's buffer is free once the previous bulk copies out of it have read it
-#if B2D_STG_MODE == 6
-              // pair buffer = the smem image of a 3-D TMA box {132, 2, 8}: [8 rows][2 chunks of 128 columns][132 floats]
-              // (row pitch 1056 B, chunk pitch 528 B: the 4 pad floats of a chunk lie outside dimension 0 of the
-              // tensor map and are never written) -- padded rows for conflict-free fragment stores AND a single
-              // TMA op per 8 full-width rows, issued by lane 0 of warp g = 0
-              if (g == 0) {
-                if (lane == 0) ptx::tma_store_wait_read();
-                __syncwarp();
-                ptx::bar_arrive(bar_free, 64);
-              } else {
-                ptx::bar_sync(bar_free, 64);
-              }
-#elif B2D_STG_MODE >= 3
-              ptx::tma_store_wait_read();
-              __syncwarp();
-              ptx::bar_sync(bar_free, 64);
-#else
-              if (g == 0) {
-                ptx::tma_store_wait_read();
-                __syncwarp();
-                ptx::bar_arrive(bar_free, 64);
-              } else {
-                ptx::bar_sync(bar_free, 64);
-              }
-#endif
-#if B2D_STG_MODE == 6
-              uint8_t* rowp = pbuf + quad * TC_STG_ROW + g * 528 + 8 * tq;
-#else
-              uint8_t* rowp = pbuf + quad * TC_STG_ROW + (g * 128 + 2 * tq) * 4;
-#endif
-#pragma unroll
-              for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(rowp + 32 * i) = make_float2(v[2 * i], v[2 * i + 1]);
-              ptx::fence_proxy_async_smem();
-              const int64_t orow0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + 8 * j;
-              const int64_t ocol0 = static_cast<int64_t>(n_blk) * TC_BN;
-#if B2D_STG_MODE == 6
-              if (g == 1) {
-                ptx::bar_arrive(bar_full, 64);
-              } else {
-                ptx::bar_sync(bar_full, 64);
-                if (lane == 0) {
-                  ptx::tma_store_3d(&tmap_d, pbuf, 0, 2 * n_blk, static_cast<int32_t>(orow0), pol_st);
-                  ptx::tma_store_commit();
-                }
-                __syncwarp();
-              }
-#elif B2D_STG_MODE >= 3
-              ptx::bar_sync(bar_full, 64);
-              {
-#if B2D_STG_MODE == 3   // both warps: 4 rows x 4 segments of 256 B each
-                const int br = 4 * g + (lane >> 2), seg = lane & 3, segb = 256;
-                const bool on = lane < 16;
-#else                   // both warps: 4 rows x 1 KB each
-                const int br = 4 * g + lane, seg = 0, segb = 1024;
-                const bool on = lane < 4;
-#endif
-                const int64_t ocol = ocol0 + seg * 64;
-                const int64_t left = (p.n - ocol) * 4;
-                if (on && orow0 + br < p.m && left > 0)
-                  ptx::bulk_store(p.dist + (orow0 + br) * p.ldd + ocol, pbuf + br * TC_STG_ROW + seg * 256,
-                                  static_cast<uint32_t>(left < segb ? left : segb), pol_st);
-                ptx::tma_store_commit();
-              }
-#else
-              if (g == 1) {
-                ptx::bar_arrive(bar_full, 64);
-              } else {
-                ptx::bar_sync(bar_full, 64);
-#if B2D_STG_MODE == 1   // lane -> (row, 256-byte segment): 8 rows x 4 adjacent segments per instruction
-                const int br = lane >> 2, seg = lane & 3, segb = 256;
-                const bool on = true;
-#else                   // 8 rows x 1 KB
-                const int br = lane, seg = 0, segb = 1024;
-                const bool on = lane < 8;
-#endif
-                const int64_t ocol = ocol0 + seg * 64;
-                const int64_t left = (p.n - ocol) * 4;  // bytes of this row segment inside the matrix (n % 4 == 0)
-                if (on && orow0 + br < p.m && left > 0)
-                  ptx::bulk_store(p.dist + (orow0 + br) * p.ldd + ocol, pbuf + br * TC_STG_ROW + seg * 256,
-                                  static_cast<uint32_t>(left < segb ? left : segb), pol_st);
-                ptx::tma_store_commit();
-              }
-#endif
-#endif
-            }
-          }
-          continue;
-        }
-#endif
         // the 4 tile rows this thread owns: 32q + quad + 8j, j = 0..3  (j = 2*rh + (0|1))
         const int64_t row0 = static_cast<int64_t>(mt) * TC_BM + q * 32 + quad;
         uint64_t ta2[4], cfr2[4];
@@ -1099,8 +781,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   }
 
-  if (kTma && warp >= 2) {  // (experimental modes: every lane of the issuing warps may own bulk groups)
-    ptx::tma_store_wait_all();
+  if (kTma && warp >= 2) {
+    if (lane == 0) ptx::tma_store_wait_all();
     __syncwarp();
   }
   ptx::tc_fence_before();
