@@ -255,8 +255,12 @@ def gpu_baselines_pairwise(x, y, out, m, n, k, ours_ms, torch, steps=5, warm=2):
     probe = {}
     for mod in ("pylibraft.distance", "cuvs.distance"):
         try:
-            __import__(mod)
-            probe[mod] = "importable (not timed: unexpected on this image)"
+            mobj = __import__(mod, fromlist=["x"])
+            where = os.path.abspath(getattr(mobj, "__file__", "") or "")
+            if where.startswith(ROOT):
+                probe[mod] = "only this repo's alias package (no RAFT / cuVS wheel on the box)"
+            else:
+                probe[mod] = "importable at " + where + " (not timed: unexpected on this image)"
         except Exception as e:  # noqa: BLE001
             probe[mod] = "not importable: " + type(e).__name__
     res["reference_gpu_kernels_probe"] = probe

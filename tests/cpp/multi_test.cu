@@ -76,11 +76,21 @@ int main(int argc, char** argv)
         // a different index is only acceptable for an fp32-inseparable tie
         double da = 0, db = 0;
         for (int t = 0; t < k; ++t) { double a = (double)hx[i * k + t] - hy[(int64_t)got[i].key * k + t]; double b = (double)hx[i * k + t] - hy[(int64_t)ref[i].key * k + t]; da += a * a; db += b * b; }
-        if (std::fabs(da - db) > 1e-6 * db) ++bad;
+        if (std::fabs(da - db) > 1e-4 * db + 4e-6 * (da + db)) ++bad;   // (the engine's 1e-4 bar: tensor-path vs direct fp32 finalists)
       }
-      const double rel = std::fabs((double)got[i].value - ref[i].value) / std::fmax(ref[i].value, 1e-6);
+      // the single-device call may finish through the tensor-path kernel (3-term split: ~5e-5 of d, and an absolute
+      // error ~1e-6 |x|^2 on near-duplicate pairs) while a sub-chunked shard search re-measures its finalists directly
+      // in fp32: both are inside the engine's 1e-4 bar, so that is the tolerance here
+      double xn = 0;
+      for (int t = 0; t < k; ++t) xn += (double)hx[i * k + t] * hx[i * k + t];
+      const double diff = std::fabs((double)got[i].value - ref[i].value);
+      const double rel  = diff / std::fmax(ref[i].value, 1e-6);
+      if (diff <= 4e-6 * xn) continue;
       if (rel > worst) worst = rel;
-      if (rel > 1e-5) ++bad;
+      if (rel > 1e-4) {
+        if (bad < 6) std::printf("  dev %d row %lld: got (%d, %g) ref (%d, %g)\n", g, (long long)i, got[i].key, got[i].value, ref[i].key, ref[i].value);
+        ++bad;
+      }
     }
   }
   std::printf("devices %d  max rel diff of the values vs the single-device call %.3g\n", G, worst);
