@@ -27,8 +27,9 @@ inline void b2d_check(int status)
 template <typename T>
 constexpr int b2d_dtype()
 {
-  static_assert(std::is_same<T, float>::value, "raft_b200: fp32 inputs (fp16 through the C ABI)");
-  return B2D_F32;
+  static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value,
+                "raft_b200: float or double (fp16 inputs through the C ABI)");
+  return std::is_same<T, double>::value ? B2D_F64 : B2D_F32;
 }
 }  // namespace detail
 

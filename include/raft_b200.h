@@ -61,15 +61,19 @@ enum {
   B2D_Canberra            = 8,
   B2D_LpUnexpanded        = 9,
   B2D_CorrelationExpanded = 10,
+  B2D_JaccardExpanded     = 11, /* 1 - <x,y> / (|x|^2 + |y|^2 - <x,y>): Jaccard distance on indicator data */
   B2D_HellingerExpanded   = 12,
+  B2D_BrayCurtis          = 14, /* sum |x - y| / sum |x + y| */
   B2D_JensenShannon       = 15,
   B2D_HammingUnexpanded   = 16,
   B2D_KLDivergence        = 17,
-  B2D_RusselRaoExpanded   = 18
+  B2D_RusselRaoExpanded   = 18,
+  B2D_DiceExpanded        = 19  /* 1 - 2 <x,y> / (|x|^2 + |y|^2): Dice dissimilarity on indicator data */
 };
 
-/* element types of x / y (dist is always fp32) */
-enum { B2D_F32 = 0, B2D_F16 = 1 };
+/* element types of x / y: fp32 (dist fp32), fp16 (fp32 accumulate, dist fp32), fp64 (dist fp64: a SIMT double-precision
+ * path for every metric; workspace = per-row statistics, 16 (m + n) bytes) */
+enum { B2D_F32 = 0, B2D_F16 = 1, B2D_F64 = 2 };
 
 /* raft::KeyValuePair<int,float> (cpp/include/raft/core/kvp.hpp:20-62) */
 typedef struct {
@@ -100,7 +104,7 @@ size_t b2d_pairwise_workspace_bytes(int metric, int dtype, int64_t m, int64_t n,
  * leading dimensions ldx, ldy, ldd (elements, >= k / k / n); row_major == 0: Fortran order
  * (ld >= m / n / m).  x and y may alias.  metric_arg = p of LpUnexpanded. */
 int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, int64_t ldx,
-                          const void* y, int64_t ldy, float* dist, int64_t ldd, int64_t m,
+                          const void* y, int64_t ldy, void* dist /* float*, or double* for B2D_F64 */, int64_t ldd, int64_t m,
                           int64_t n, int64_t k, int row_major, float metric_arg, void* workspace,
                           size_t workspace_bytes);
 

@@ -44,10 +44,11 @@ class DistanceType(enum.IntEnum):
 
 EXPANDED = (DistanceType.L2Expanded, DistanceType.L2SqrtExpanded, DistanceType.CosineExpanded,
             DistanceType.CorrelationExpanded, DistanceType.InnerProduct, DistanceType.HellingerExpanded,
-            DistanceType.RusselRaoExpanded)
+            DistanceType.RusselRaoExpanded, DistanceType.JaccardExpanded, DistanceType.DiceExpanded)
 UNEXPANDED = (DistanceType.L1, DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded,
               DistanceType.Linf, DistanceType.Canberra, DistanceType.LpUnexpanded,
-              DistanceType.HammingUnexpanded, DistanceType.KLDivergence, DistanceType.JensenShannon)
+              DistanceType.HammingUnexpanded, DistanceType.KLDivergence, DistanceType.JensenShannon,
+              DistanceType.BrayCurtis)
 
 
 def row_norm_sq(x: np.ndarray) -> np.ndarray:
@@ -96,6 +97,19 @@ def _block(x64, y64, metric, p):
     if metric == DistanceType.RusselRaoExpanded:
         k = x64.shape[1]
         return (k - x64 @ y64.T) / k
+    if metric in (DistanceType.JaccardExpanded, DistanceType.DiceExpanded):
+        # [RECALLED] expanded forms on a = <x,y>, s = |x|^2 + |y|^2 (the reference's sparse / dense ops; on
+        # indicator data they are scipy's jaccard / dice):  Jaccard 1 - a / (s - a),  Dice 1 - 2a / s;  0/0 -> 0
+        a = x64 @ y64.T
+        s_ = np.einsum("ij,ij->i", x64, x64)[:, None] + np.einsum("ij,ij->i", y64, y64)[None, :]
+        den = s_ - a if metric == DistanceType.JaccardExpanded else s_
+        num = a if metric == DistanceType.JaccardExpanded else 2.0 * a
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(den > 0.0, np.maximum(1.0 - num / den, 0.0), 0.0)
+    if metric == DistanceType.BrayCurtis:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return (np.abs(x64[:, None, :] - y64[None, :, :]).sum(axis=2) /
+                    np.abs(x64[:, None, :] + y64[None, :, :]).sum(axis=2))
     if metric == DistanceType.HammingUnexpanded:
         return (x64[:, None, :] != y64[None, :, :]).mean(axis=2)
     if metric in (DistanceType.KLDivergence, DistanceType.JensenShannon):
@@ -139,7 +153,8 @@ def pairwise_distance(x, y, metric=DistanceType.L2Expanded, metric_arg: float = 
     out = np.empty((m, n), dtype=np.float64)
     if metric in EXPANDED + (DistanceType.L2Unexpanded, DistanceType.L2SqrtUnexpanded):
         block = max(block, 2048)
-    elif metric in (DistanceType.KLDivergence, DistanceType.JensenShannon, DistanceType.HammingUnexpanded):
+    elif metric in (DistanceType.KLDivergence, DistanceType.JensenShannon, DistanceType.HammingUnexpanded,
+                    DistanceType.BrayCurtis):
         block = min(block, 128)
     for i0 in range(0, m, block):
         for j0 in range(0, n, block):

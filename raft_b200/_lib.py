@@ -19,7 +19,7 @@ SYMBOLS = [
 ]
 
 B2D_OK, B2D_ERR_INVALID_ARG, B2D_ERR_CUDA, B2D_ERR_UNSUPPORTED, B2D_ERR_WORKSPACE = range(5)
-B2D_F32, B2D_F16 = 0, 1
+B2D_F32, B2D_F16, B2D_F64 = 0, 1, 2
 
 
 class RaftB200Error(RuntimeError):

@@ -18,6 +18,7 @@
 #include "prep.cuh"
 #include "unexpanded_simt.cuh"
 #include "stats.cuh"
+#include "fp64_simt.cuh"
 
 namespace b2d {
 
@@ -182,13 +183,14 @@ static bool is_expanded(int metric)
 {
   return metric == B2D_L2Expanded || metric == B2D_L2SqrtExpanded || metric == B2D_CosineExpanded ||
          metric == B2D_CorrelationExpanded || metric == B2D_InnerProduct || metric == B2D_HellingerExpanded ||
-         metric == B2D_RusselRaoExpanded;
+         metric == B2D_RusselRaoExpanded || metric == B2D_JaccardExpanded || metric == B2D_DiceExpanded;
 }
 static bool is_unexpanded(int metric)
 {
   return metric == B2D_L1 || metric == B2D_L2Unexpanded || metric == B2D_L2SqrtUnexpanded ||
          metric == B2D_Linf || metric == B2D_Canberra || metric == B2D_LpUnexpanded ||
-         metric == B2D_HammingUnexpanded || metric == B2D_KLDivergence || metric == B2D_JensenShannon;
+         metric == B2D_HammingUnexpanded || metric == B2D_KLDivergence || metric == B2D_JensenShannon ||
+         metric == B2D_BrayCurtis;
 }
 
 template <typename T>
@@ -248,6 +250,8 @@ static int launch_tc_store(cudaStream_t s, const CUtensorMap& ma, const CUtensor
 {
   if (post == POST_NONE) return launch_tc_inst<kRes, EPI_STORE, POST_NONE, kTma>(s, ma, mb, md, mr, p, grid);
   if (post == POST_CLAMP) return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP, kTma>(s, ma, mb, md, mr, p, grid);
+  if (post == POST_JACCARD) return launch_tc_inst<kRes, EPI_STORE, POST_JACCARD, false>(s, ma, mb, md, mr, p, grid);
+  if (post == POST_DICE) return launch_tc_inst<kRes, EPI_STORE, POST_DICE, false>(s, ma, mb, md, mr, p, grid);
   return launch_tc_inst<kRes, EPI_STORE, POST_CLAMP_SQRT, kTma>(s, ma, mb, md, mr, p, grid);
 }
 
@@ -343,7 +347,7 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
   // 16-byte aligned base and row pitch and n % 4 == 0; ragged or unaligned outputs take the direct
   // register->global path
   bool tma = (reinterpret_cast<uintptr_t>(p.dist) % 16 == 0) && (p.ldd % 4 == 0) && (p.n % 4 == 0) &&
-             p.acc_mode == 0;  // the K-chunked read-modify-write epilogue lives in the direct path
+             p.acc_mode == 0 && post < POST_JACCARD;  // the K-chunked read-modify-write epilogue lives in the direct path
   // k <= 128 with an aligned output: the CTA-pair kernel (full-width output rows, expanded_tc2.cuh)
   if (tma && resident && p.sel_s <= 1 && p.run_flag == nullptr && sms >= 2 && g_pair_kernel.load(std::memory_order_relaxed))
     return launch_tc2(s, w, p, k, post, sms);
@@ -540,6 +544,45 @@ __global__ void __launch_bounds__(256) row_argmin_kernel(int* out, const float* 
 
 using namespace b2d;
 
+// fp64 path: one SIMT kernel per metric (fp64_simt.cuh)
+template <int kMetric>
+static int launch_f64_inst(cudaStream_t s, const F64Params& p, int64_t tiles)
+{
+  f64_pairwise_kernel<kMetric><<<static_cast<unsigned>(tiles), 256, 0, s>>>(p);
+  B2D_CUDA(cudaGetLastError());
+  return B2D_OK;
+}
+
+static int pairwise_f64(cudaStream_t s, int metric, const double* x, int64_t xrs, int64_t xcs, const double* y, int64_t yrs,
+                        int64_t ycs, double* dist, int64_t ldd, int64_t m, int64_t n, int64_t k, int swapped, double metric_arg,
+                        void* workspace, size_t workspace_bytes)
+{
+  const size_t need = align_up(static_cast<size_t>(m + n) * 16, 1024);
+  if (!workspace || workspace_bytes < need) return fail(B2D_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+  double* xs = static_cast<double*>(workspace);
+  double* ys = xs + 2 * m;
+  f64_row_stats_kernel<<<static_cast<unsigned>((m + 7) / 8), 256, 0, s>>>(xs, x, xrs, xcs, m, static_cast<int>(k));
+  f64_row_stats_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(ys, y, yrs, ycs, n, static_cast<int>(k));
+  B2D_CUDA(cudaGetLastError());
+  F64Params p;
+  p.x = x; p.y = y; p.dist = dist; p.xrs = xrs; p.xcs = xcs; p.yrs = yrs; p.ycs = ycs; p.ldd = ldd; p.m = m; p.n = n;
+  p.k = static_cast<int>(k); p.metric = metric; p.swapped = swapped; p.p = metric_arg; p.inv_p = 1.0 / metric_arg;
+  p.xs = xs; p.ys = ys;
+  p.tiles_n = static_cast<int>((n + F64_T - 1) / F64_T);
+  const int64_t tiles = ((m + F64_T - 1) / F64_T) * p.tiles_n;
+  switch (metric) {
+#define B2D_F64_CASE(M) case M: return launch_f64_inst<M>(s, p, tiles);
+    B2D_F64_CASE(B2D_L2Expanded) B2D_F64_CASE(B2D_L2SqrtExpanded) B2D_F64_CASE(B2D_CosineExpanded) B2D_F64_CASE(B2D_L1)
+    B2D_F64_CASE(B2D_L2Unexpanded) B2D_F64_CASE(B2D_L2SqrtUnexpanded) B2D_F64_CASE(B2D_InnerProduct) B2D_F64_CASE(B2D_Linf)
+    B2D_F64_CASE(B2D_Canberra) B2D_F64_CASE(B2D_LpUnexpanded) B2D_F64_CASE(B2D_CorrelationExpanded)
+    B2D_F64_CASE(B2D_JaccardExpanded) B2D_F64_CASE(B2D_HellingerExpanded) B2D_F64_CASE(B2D_BrayCurtis)
+    B2D_F64_CASE(B2D_JensenShannon) B2D_F64_CASE(B2D_HammingUnexpanded) B2D_F64_CASE(B2D_KLDivergence)
+    B2D_F64_CASE(B2D_RusselRaoExpanded) B2D_F64_CASE(B2D_DiceExpanded)
+#undef B2D_F64_CASE
+    default: return fail(B2D_ERR_UNSUPPORTED, "metric");
+  }
+}
+
 extern "C" {
 
 int b2d_profile_begin(int capacity)
@@ -604,17 +647,20 @@ const char* b2d_last_error(void) { return g_err.c_str(); }
 
 size_t b2d_pairwise_workspace_bytes(int metric, int dtype, int64_t m, int64_t n, int64_t k)
 {
-  if (dtype != B2D_F32 && dtype != B2D_F16) return static_cast<size_t>(-1);
+  if (dtype != B2D_F32 && dtype != B2D_F16 && dtype != B2D_F64) return static_cast<size_t>(-1);
   if (m < 0 || n < 0 || k < 0) return static_cast<size_t>(-1);
+  if (dtype == B2D_F64)   // per-row (sum, sum of squares) of x and y
+    return (is_expanded(metric) || is_unexpanded(metric)) ? align_up(static_cast<size_t>(m + n) * 16, 1024) : static_cast<size_t>(-1);
   if (is_unexpanded(metric)) return dtype == B2D_F32 ? 0 : static_cast<size_t>(-1);
   if (!is_expanded(metric)) return static_cast<size_t>(-1);
   return tc_layout(nullptr, m, n, k, false).bytes;
 }
 
 int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, int64_t ldx, const void* y,
-                          int64_t ldy, float* dist, int64_t ldd, int64_t m, int64_t n, int64_t k,
+                          int64_t ldy, void* dist_v, int64_t ldd, int64_t m, int64_t n, int64_t k,
                           int row_major, float metric_arg, void* workspace, size_t workspace_bytes)
 {
+  float* dist = static_cast<float*>(dist_v);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "negative extent");
   if (m == 0 || n == 0) return B2D_OK;
@@ -628,8 +674,15 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
   }
   if (!is_expanded(metric) && !is_unexpanded(metric))
     return fail(B2D_ERR_UNSUPPORTED, "metric " + std::to_string(metric) + " is not on the B200 distance path");
-  if (dtype != B2D_F32 && dtype != B2D_F16) return fail(B2D_ERR_UNSUPPORTED, "dtype");
+  if (dtype != B2D_F32 && dtype != B2D_F16 && dtype != B2D_F64) return fail(B2D_ERR_UNSUPPORTED, "dtype");
   if (metric == B2D_LpUnexpanded && !(metric_arg > 0.f)) return fail(B2D_ERR_INVALID_ARG, "LpUnexpanded needs p > 0");
+  if (dtype == B2D_F64) {   // double in / double out: the SIMT fp64 path, every metric
+    if (row_major)
+      return pairwise_f64(s, metric, static_cast<const double*>(x), ldx, 1, static_cast<const double*>(y), ldy, 1,
+                          static_cast<double*>(dist_v), ldd, m, n, k, 0, metric_arg, workspace, workspace_bytes);
+    return pairwise_f64(s, metric, static_cast<const double*>(y), 1, ldy, static_cast<const double*>(x), 1, ldx,
+                        static_cast<double*>(dist_v), ldd, n, m, k, 1, metric_arg, workspace, workspace_bytes);
+  }
 
   // Fortran order: D^T (row-major [n,m]) = metric(y_j, x_i).  Every metric here is symmetric except
   // KLDivergence, which switches to the kernel with the operand roles exchanged (UX_KL_REV).
@@ -653,6 +706,8 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     else if (metric == B2D_CorrelationExpanded) { mode = PREP_COSINE; center = 1; }
     else if (metric == B2D_HellingerExpanded) { mode = PREP_INNER; post = POST_CLAMP_SQRT; xform = 1; coef_mul = -1.f; tx_const = 1.f; }
     else if (metric == B2D_RusselRaoExpanded) { mode = PREP_INNER; coef_mul = -1.f / static_cast<float>(k); tx_const = 1.f; }
+    else if (metric == B2D_JaccardExpanded) { mode = PREP_INNER_NORM; post = POST_JACCARD; }
+    else if (metric == B2D_DiceExpanded) { mode = PREP_INNER_NORM; post = POST_DICE; }
     else { mode = PREP_INNER; }
     int rc = dtype == B2D_F32
                ? launch_prep<float>(s, w, xa, xrs, xcs, ma, ya, yrs, ycs, na, k, nullptr, nullptr, mode, center, xform,
@@ -670,7 +725,7 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     const int nkb_total = static_cast<int>((k + 31) / 32);
     constexpr int kChunk = 8;
     ProfileScope prof(s);  // the main kernel(s) only: the operand preparation above is outside
-    if (nkb_total > 10) {
+    if (nkb_total > 10 && post < POST_JACCARD) {  // (the ratio metrics need the whole inner product at once)
       for (int kb0 = 0; kb0 < nkb_total; kb0 += kChunk) {
         const int nk = nkb_total - kb0 < kChunk ? nkb_total - kb0 : kChunk;
         p.acc_mode   = kb0 == 0 ? 1 : (kb0 + nk >= nkb_total ? 3 : 2);
@@ -706,6 +761,7 @@ int b2d_pairwise_distance(void* stream, int metric, int dtype, const void* x, in
     case B2D_KLDivergence:
       return row_major ? launch_ux_inst<UX_KL>(s, p, tiles) : launch_ux_inst<UX_KL_REV>(s, p, tiles);
     case B2D_JensenShannon: return launch_ux_inst<UX_JS>(s, p, tiles);
+    case B2D_BrayCurtis: return launch_ux_inst<UX_BRAYCURTIS>(s, p, tiles);
     default: return launch_ux_inst<UX_LP>(s, p, tiles);
   }
 }

@@ -68,7 +68,18 @@ constexpr int TC_EPI_WARPS   = 8;
 constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
 
 enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1, EPI_TOPK = 2 };
-enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2 };
+enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2,
+                    POST_JACCARD = 3,  // d = 1 - a / (s - a), a = <x,y>, s = |x|^2 + |y|^2 (0/0 -> 0): direct-store path only
+                    POST_DICE    = 4 };  // d = 1 - 2 a / s
+
+// ratio metrics on the tensor path: a = acc * c (the inner product), s = t_x + t_y (the squared norms)
+template <int kPost>
+__device__ __forceinline__ float post_ratio(float a, float s)
+{
+  const float den = kPost == POST_JACCARD ? s - a : s;
+  const float num = kPost == POST_JACCARD ? a : 2.f * a;
+  return den > 0.f ? fmaxf(1.f - __fdividef(num, den), 0.f) : 0.f;
+}
 
 struct TcParams {
   int64_t m, n;
@@ -627,9 +638,21 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               t0 = tb2;
               t1 = tb2;
             }
-            uint64_t w0 = fma2(a0, cfr2[2 * rh], t0), w1 = fma2(a1, cfr2[2 * rh + 1], t1);
-            unpk(w0, v[4 * i], v[4 * i + 1]);
-            unpk(w1, v[4 * i + 2], v[4 * i + 3]);
+            if (kEpi == EPI_STORE && kPost >= POST_JACCARD) {
+              float a00, a01, a10, a11, s00, s01, s10, s11;
+              unpk(mul2(a0, cfr2[2 * rh]), a00, a01);
+              unpk(mul2(a1, cfr2[2 * rh + 1]), a10, a11);
+              unpk(t0, s00, s01);
+              unpk(t1, s10, s11);
+              v[4 * i]     = post_ratio<kPost>(a00, s00);
+              v[4 * i + 1] = post_ratio<kPost>(a01, s01);
+              v[4 * i + 2] = post_ratio<kPost>(a10, s10);
+              v[4 * i + 3] = post_ratio<kPost>(a11, s11);
+            } else {
+              uint64_t w0 = fma2(a0, cfr2[2 * rh], t0), w1 = fma2(a1, cfr2[2 * rh + 1], t1);
+              unpk(w0, v[4 * i], v[4 * i + 1]);
+              unpk(w1, v[4 * i + 2], v[4 * i + 3]);
+            }
           }
           if (f < 3) {  // r / rc are dead: fetch the next fragment while this one is stored / reduced
             const int nf       = f + 1;
@@ -675,7 +698,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 }
               }
             }
-            if (kPost != POST_NONE && (p.acc_mode == 0 || p.acc_mode == 3)) {
+            if (kPost != POST_NONE && kPost < POST_JACCARD && (p.acc_mode == 0 || p.acc_mode == 3)) {
 #pragma unroll
               for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
               if (p.diag_zero) {

@@ -29,7 +29,8 @@
 
 namespace b2d {
 
-enum PrepMode : int { PREP_L2 = 0, PREP_COSINE = 1, PREP_INNER = 2 };
+enum PrepMode : int { PREP_L2 = 0, PREP_COSINE = 1, PREP_INNER = 2,
+                      PREP_INNER_NORM = 3 };  // inner product with t = |row|^2 (Jaccard / Dice: ratio epilogues)
 
 struct PrepSide {
   const void* src;  // float or half
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   const int ex = scale_exponent(__uint_as_float(p.gmax[0]));
   const int ey = scale_exponent(__uint_as_float(p.gmax[1]));
   if (which == 0 && r == 0 && lane == 0) {
-    const float c = p.mode == PREP_L2 ? -2.f : (p.mode == PREP_COSINE ? -1.f : 1.f);
+    const float c = p.mode == PREP_L2 ? -2.f : (p.mode == PREP_COSINE ? -1.f : 1.f);  // (PREP_INNER / PREP_INNER_NORM: +1)
     *p.coef       = c * p.coef_mul * ldexpf(1.f, -ex) * ldexpf(1.f, -ey);
   }
   float mean, amax;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
     atomicExch(p.has_lo, 1u);
   if (lane == 0) {
     float t;
-    if (p.mode == PREP_L2) t = sd.ext_norm_sq ? sd.ext_norm_sq[r] : static_cast<float>(ss);
+    if (p.mode == PREP_L2 || p.mode == PREP_INNER_NORM) t = sd.ext_norm_sq ? sd.ext_norm_sq[r] : static_cast<float>(ss);
     else if (p.mode == PREP_COSINE) t = which == 0 ? 1.f : 0.f;
     else t = which == 0 ? p.tx_const : 0.f;
     sd.tvec[r] = t;

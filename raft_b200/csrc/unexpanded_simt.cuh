@@ -25,7 +25,8 @@ constexpr int UX_TMA_SMEM_BYTES = UX_TMA_STAGES * (UX_BM + UX_BN) * UX_KB * 4 + 
 
 enum UxMetric : int { UX_L1 = 0, UX_L2 = 1, UX_L2SQRT = 2, UX_LINF = 3, UX_CANBERRA = 4, UX_LP = 5,
                       UX_HAMMING = 6, UX_KL = 7, UX_JS = 8,
-                      UX_KL_REV = 9 };  // KL with the operand roles swapped: sum b log(b/a) (Fortran-order inputs)
+                      UX_KL_REV = 9,
+                      UX_BRAYCURTIS = 10 };  // sum |a - b| / sum |a + b|: the denominator rides in a second accumulator  // KL with the operand roles swapped: sum b log(b/a) (Fortran-order inputs)
 
 struct UxParams {
   const float* x;
@@ -71,6 +72,8 @@ __device__ __forceinline__ void ux_acc(float& acc, float a, float b, float p)
     // so the kernel accumulates KL(b || a) there -- the reference's !is_row_major branch did the same swap
     const float t = b * (__log2f(b) - __log2f(a));
     acc += (b == 0.f) ? 0.f : t;
+  } else if (kMetric == UX_BRAYCURTIS) {
+    acc += fabsf(a - b);  // numerator; the denominator sum |a + b| accumulates next to it (ux_den)
   } else if (kMetric == UX_JS) {
     // sum x log(x/m) + y log(y/m), m = (x+y)/2; 0 log 0 = 0
     const float lm = __log2f(0.5f * (a + b));
@@ -81,6 +84,12 @@ __device__ __forceinline__ void ux_acc(float& acc, float a, float b, float p)
     const float d = fabsf(a - b);
     acc += exp2f(p * __log2f(d));  // d == 0 -> log2 = -inf -> exp2 = 0
   }
+}
+
+template <int kMetric>
+__device__ __forceinline__ void ux_den(float& den, float a, float b)
+{
+  if (kMetric == UX_BRAYCURTIS) den += fabsf(a + b);
 }
 
 template <int kMetric>
@@ -126,11 +135,12 @@ __global__ void __launch_bounds__(UX_THREADS, 1) unexpanded_simt_kernel(const Ux
   const int64_t m0   = (tile / p.tiles_n) * UX_BM;
   const int64_t n0   = (tile % p.tiles_n) * UX_BN;
 
-  float acc[8][8];
+  constexpr int kD = kMetric == UX_BRAYCURTIS ? 8 : 1;  // second accumulator only where a metric needs one
+  float acc[8][8], den[kD][kD];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) { acc[i][j] = 0.f; den[i % kD][j % kD] = 0.f; }
 
   const int nkb = (p.k + UX_KB - 1) / UX_KB;
   float4 gx[4], gy[4];
@@ -178,6 +188,10 @@ __global__ void __launch_bounds__(UX_THREADS, 1) unexpanded_simt_kernel(const Ux
           ux_acc<kMetric>(acc[i][j], a[i].y, b.y, p.p);
           ux_acc<kMetric>(acc[i][j], a[i].z, b.z, p.p);
           ux_acc<kMetric>(acc[i][j], a[i].w, b.w, p.p);
+          ux_den<kMetric>(den[i % kD][j % kD], a[i].x, b.x);
+          ux_den<kMetric>(den[i % kD][j % kD], a[i].y, b.y);
+          ux_den<kMetric>(den[i % kD][j % kD], a[i].z, b.z);
+          ux_den<kMetric>(den[i % kD][j % kD], a[i].w, b.w);
         }
       }
     }
@@ -194,7 +208,9 @@ __global__ void __launch_bounds__(UX_THREADS, 1) unexpanded_simt_kernel(const Ux
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int64_t gj = n0 + tx + 16 * j;
-      if (gj < p.n) __stcs(p.dist + gi * p.ldd + gj, ux_fin<kMetric>(acc[i][j], p.inv_p));
+      if (gj < p.n)
+        __stcs(p.dist + gi * p.ldd + gj,
+               kMetric == UX_BRAYCURTIS ? acc[i][j] / den[i % kD][j % kD] : ux_fin<kMetric>(acc[i][j], p.inv_p));
     }
   }
 }
@@ -270,13 +286,15 @@ unexpanded_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   // L2 / L2Sqrt: packed f32x2 math (FADD2 + FFMA2: one issue slot per pair-element instead of two);
   // every output keeps an (even-k, odd-k) pair of partial sums that is folded at the end.
   constexpr bool kPackedL2 = (kMetric == UX_L2 || kMetric == UX_L2SQRT);
-  float acc[8][8];
+  constexpr int kD = kMetric == UX_BRAYCURTIS ? 8 : 1;
+  float acc[8][8], den[kD][kD];
   uint64_t acc2[kPackedL2 ? 8 : 1][kPackedL2 ? 8 : 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[i][j] = 0.f;
+      den[i % kD][j % kD] = 0.f;
       if (kPackedL2) acc2[i % (kPackedL2 ? 8 : 1)][j % (kPackedL2 ? 8 : 1)] = 0ull;
     }
 
@@ -324,6 +342,10 @@ unexpanded_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             ux_acc<kMetric>(acc[i][j], a[i].y, b.y, p.p);
             ux_acc<kMetric>(acc[i][j], a[i].z, b.z, p.p);
             ux_acc<kMetric>(acc[i][j], a[i].w, b.w, p.p);
+            ux_den<kMetric>(den[i % kD][j % kD], a[i].x, b.x);
+            ux_den<kMetric>(den[i % kD][j % kD], a[i].y, b.y);
+            ux_den<kMetric>(den[i % kD][j % kD], a[i].z, b.z);
+            ux_den<kMetric>(den[i % kD][j % kD], a[i].w, b.w);
           }
         }
       }
@@ -350,7 +372,9 @@ unexpanded_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int64_t gj = n0 + tx + 16 * j;
-      if (gj < p.n) __stcs(p.dist + gi * p.ldd + gj, ux_fin<kMetric>(acc[i][j], p.inv_p));
+      if (gj < p.n)
+        __stcs(p.dist + gi * p.ldd + gj,
+               kMetric == UX_BRAYCURTIS ? acc[i][j] / den[i % kD][j % kD] : ux_fin<kMetric>(acc[i][j], p.inv_p));
     }
   }
 }

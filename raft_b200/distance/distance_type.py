@@ -49,12 +49,15 @@ DISTANCE_TYPES = {
     "hamming": DistanceType.HammingUnexpanded,
     "kl_divergence": DistanceType.KLDivergence,
     "russellrao": DistanceType.RusselRaoExpanded,
+    "jaccard": DistanceType.JaccardExpanded,
+    "dice": DistanceType.DiceExpanded,
+    "braycurtis": DistanceType.BrayCurtis,
 }
 
 SUPPORTED_DISTANCES = sorted(DISTANCE_TYPES)
 
-# metrics of the reference enum that are outside this engine's scope
-UNSUPPORTED = {"jaccard", "haversine", "braycurtis", "dice"}
+# metric of the reference enum that is outside this engine's scope (2-d lat/lon only in the reference)
+UNSUPPORTED = {"haversine"}
 
 
 def resolve_metric(metric) -> DistanceType:

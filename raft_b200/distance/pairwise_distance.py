@@ -12,7 +12,7 @@ from .. import _lib
 from ..common import auto_convert_output, auto_sync_handle, cai_wrapper, device_ndarray
 from .distance_type import DistanceType, resolve_metric
 
-_DT = {np.dtype(np.float32): _lib.B2D_F32, np.dtype(np.float16): _lib.B2D_F16}
+_DT = {np.dtype(np.float32): _lib.B2D_F32, np.dtype(np.float16): _lib.B2D_F16, np.dtype(np.float64): _lib.B2D_F64}
 
 
 def _layout(w: cai_wrapper):
@@ -41,7 +41,8 @@ def pairwise_distance(X, Y, out=None, metric="euclidean", p=2.0, handle=None):
     """Compute pairwise distances between X [m,k] and Y [n,k].
 
     Parameters mirror pylibraft: X, Y any ``__cuda_array_interface__`` objects of the same
-    float32 (or float16) dtype and memory order; ``out`` optional [m,n] float32 array (written in
+    float32 / float64 (or float16) dtype and memory order; ``out`` optional [m,n] array of the inputs' dtype (float32 for
+    float16 inputs; written in
     place and returned); ``metric`` a string from ``DISTANCE_TYPES`` or a ``DistanceType``;
     ``p`` the Minkowski exponent; ``handle`` a ``DeviceResources`` (None: one is created and
     synchronised before returning)."""
@@ -70,16 +71,18 @@ def pairwise_distance(X, Y, out=None, metric="euclidean", p=2.0, handle=None):
     else:
         ldx, ldy = max(ldx, k), max(ldy, k)
 
+    out_dtype = np.float64 if x_cai.dtype == np.dtype(np.float64) else np.float32
     if out is None:
         if row_major:
-            dists = device_ndarray.empty((m, n), dtype=np.float32)
+            dists = device_ndarray.empty((m, n), dtype=out_dtype)
         else:
             import torch
-            dists = device_ndarray(torch.empty((n, m), dtype=torch.float32, device="cuda").t())
+            dists = device_ndarray(torch.empty((n, m), dtype=torch.float64 if out_dtype == np.float64 else torch.float32,
+                                               device="cuda").t())
     else:
         dists = out
     d_cai = cai_wrapper(dists)
-    d_cai.validate_shape_dtype(expected_dims=2, expected_dtype=np.float32)
+    d_cai.validate_shape_dtype(expected_dims=2, expected_dtype=out_dtype)
     if d_cai.shape != (m, n):
         raise ValueError("out must have shape (%d, %d)" % (m, n))
     d_rm, ldd = _layout(d_cai)

@@ -14,6 +14,10 @@ elif what.startswith("knn"):   # knn<neighbours>, e.g. knn16: x = queries, y = d
     from raft_b200.neighbors import brute_force
     kk = int(what[3:] or 10)
     fn = lambda: brute_force.knn(y, x, k=kk, handle=h)
+elif what.endswith("_f16"):   # fp16 inputs, fp32 accumulate / output
+    out = torch.empty(m, n, device="cuda")
+    xh, yh = x.half(), y.half()
+    fn = lambda: pairwise_distance(xh, yh, out=out, metric=what[:-4], handle=h)
 else:
     out = torch.empty(m, n, device="cuda")
     fn = lambda: pairwise_distance(x, y, out=out, metric=what, handle=h)

@@ -193,7 +193,7 @@ int main()
     }
     // error convention: unsupported metric -> raft::logic_error
     bool threw = false;
-    try { raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::JaccardExpanded); }
+    try { raft::distance::pairwise_distance(handle, x, y, d, m, n, k, raft::distance::DistanceType::Haversine); }
     catch (raft::logic_error const&) { threw = true; }
     if (!threw) ++bad;
   }

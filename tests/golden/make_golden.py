@@ -60,6 +60,11 @@ def main():
     out["bool_x"], out["bool_y"] = bx, by
     out["bool_HammingUnexpanded"] = cdist(bx, by, "hamming")
     out["bool_RusselRaoExpanded"] = cdist(bx.astype(bool), by.astype(bool), "russellrao")
+    out["bool_JaccardExpanded"] = cdist(bx.astype(bool), by.astype(bool), "jaccard")
+    out["bool_DiceExpanded"] = cdist(bx.astype(bool), by.astype(bool), "dice")
+    cx = rng.random((33, 40)); cy = rng.random((27, 40))            # non-negative "abundance" vectors
+    out["count_x"], out["count_y"] = cx.astype(np.float32), cy.astype(np.float32)
+    out["count_BrayCurtis"] = cdist(out["count_x"].astype(np.float64), out["count_y"].astype(np.float64), "braycurtis")
     # reference known answers
     out["ref_argmin_in"] = np.array([0.1, 0.2, 0.3, 0.4, 0.4, 0.3, 0.2, 0.1, 0.2, 0.3, 0.5, 0.0],
                                     dtype=np.float32).reshape(3, 4)   # argmin.cu:71-72

@@ -48,7 +48,7 @@ def test_workspace_queries():
     assert L.b2d_pairwise_workspace_bytes(3, 0, 1000, 1000, 64) == 0
     ws = L.b2d_pairwise_workspace_bytes(0, 0, 1000, 1000, 64)
     assert ws >= 2 * 1000 * 64 * 4 and ws < 4 * 1000 * 64 * 4 + 65536
-    assert L.b2d_pairwise_workspace_bytes(11, 0, 10, 10, 4) == 2 ** 64 - 1   # Jaccard: not on this path
+    assert L.b2d_pairwise_workspace_bytes(13, 0, 10, 10, 4) == 2 ** 64 - 1   # Haversine: not on this path
     assert L.b2d_pairwise_workspace_bytes(16, 0, 10, 10, 4) == 0             # Hamming: SIMT path, no scratch
     assert L.b2d_fused_l2_nn_workspace_bytes(100, 200, 96) > 300 * 96 * 4
 

@@ -44,7 +44,7 @@ def test_metric_strings():
     assert resolve_metric("hamming") == DistanceType.HammingUnexpanded
     assert resolve_metric("kl_divergence") == DistanceType.KLDivergence
     with pytest.raises(ValueError):
-        resolve_metric("jaccard")
+        resolve_metric("haversine")
     assert set(DISTANCE_TYPES) >= {"l2", "l1", "cosine", "correlation", "canberra", "inner_product", "lp"}
 
 

@@ -73,7 +73,8 @@ def test_uniform_data(metric):
 
 
 @pytest.mark.parametrize("name", ["prob_KLDivergence", "prob_JensenShannon", "prob_HellingerExpanded",
-                                  "bool_HammingUnexpanded", "bool_RusselRaoExpanded"])
+                                  "bool_HammingUnexpanded", "bool_RusselRaoExpanded", "bool_JaccardExpanded",
+                                  "bool_DiceExpanded", "count_BrayCurtis"])
 def test_distribution_and_boolean_metrics(golden, name):
     # the remaining dense metrics of the enum, against the golden fixtures
     pre, metric = name.split("_")
@@ -89,6 +90,8 @@ def test_distribution_and_boolean_metrics(golden, name):
     if pre == "prob":
         a = rng.random((300, 70)); b = rng.random((260, 70))
         a /= a.sum(1, keepdims=True); b /= b.sum(1, keepdims=True)
+    elif pre == "count":
+        a = rng.random((300, 70)) * 9; b = rng.random((260, 70)) * 9
     else:
         a = (rng.random((300, 70)) > 0.5); b = (rng.random((260, 70)) > 0.5)
     a, b = a.astype(np.float32), b.astype(np.float32)
@@ -263,8 +266,6 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         pairwise_distance(a, b)
     with pytest.raises(ValueError):
-        pairwise_distance(a, a, metric="jaccard")
-    with pytest.raises(ValueError):
         pairwise_distance(a, a, metric="haversine")
     with pytest.raises(TypeError):
         pairwise_distance(a, a.double())
@@ -348,3 +349,42 @@ def test_cta_pair_kernel_self_distance_and_outliers(cta_pair_kernel):
     got = pairwise_distance(xd, xd, metric=DT.L2Expanded).copy_to_host()   # the SAME device array: x == y aliasing
     assert (np.diag(got) == 0).all()
     check(got, oracle.pairwise_distance(x, x, DT.L2Expanded))
+
+
+F64_METRICS = [DT.L2Expanded, DT.L2SqrtExpanded, DT.CosineExpanded, DT.CorrelationExpanded, DT.InnerProduct, DT.L1,
+               DT.L2Unexpanded, DT.L2SqrtUnexpanded, DT.Linf, DT.Canberra, DT.LpUnexpanded]
+
+
+@pytest.mark.parametrize("metric", F64_METRICS)
+def test_fp64_inputs_every_metric(metric):
+    """double in / double out: the SIMT fp64 path agrees with the fp64 oracle to ~1e-12."""
+    x, y = blobs(150, 131, 37)
+    x64, y64 = x.astype(np.float64) + 1e-9, y.astype(np.float64) - 1e-9      # values that fp32 cannot represent
+    out = pairwise_distance(torch.from_numpy(x64).cuda(), torch.from_numpy(y64).cuda(), metric=metric, p=3.0)
+    got = out.copy_to_host()
+    assert got.dtype == np.float64
+    ref = oracle.pairwise_distance(x64, y64, metric, 3.0)
+    assert np.allclose(got, ref, rtol=1e-11, atol=1e-9), float(np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("name", ["prob_KLDivergence", "prob_JensenShannon", "prob_HellingerExpanded", "bool_HammingUnexpanded",
+                                  "bool_RusselRaoExpanded", "bool_JaccardExpanded", "bool_DiceExpanded", "count_BrayCurtis"])
+def test_fp64_distribution_and_boolean_metrics(golden, name):
+    pre, metric = name.split("_")
+    x, y = golden[f"{pre}_x"].astype(np.float64), golden[f"{pre}_y"].astype(np.float64)
+    got = pairwise_distance(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), metric=DT[metric]).copy_to_host()
+    ref = golden[name]
+    fin = np.isfinite(ref)
+    assert (np.isinf(got) == np.isinf(ref)).all()
+    assert np.allclose(got[fin], ref[fin], rtol=1e-9, atol=1e-12)
+
+
+def test_fp64_fortran_order_and_kl_roles():
+    rng = np.random.default_rng(3)
+    a = rng.random((70, 21)); b = rng.random((50, 21))
+    a /= a.sum(1, keepdims=True); b /= b.sum(1, keepdims=True)
+    af = torch.from_numpy(a).cuda().t().contiguous().t()
+    bf = torch.from_numpy(b).cuda().t().contiguous().t()
+    for metric in (DT.KLDivergence, DT.L2Expanded, DT.CosineExpanded):
+        got = pairwise_distance(af, bf, metric=metric).copy_to_host()
+        assert np.allclose(got, oracle.pairwise_distance(a, b, metric), rtol=1e-10, atol=1e-12)
