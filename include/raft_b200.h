@@ -160,7 +160,8 @@ int b2d_fused_l2_nn_multi(int ngpu, const int* devices, void* const* streams, vo
  * pairwise_distance + raft::matrix::select_k, cpp/include/raft/matrix/select_k.cuh:73-106):
  * out_idx[i, 0..n_neighbors) = rows of y nearest to x_i in ascending (distance, index) order,
  * out_dist the squared (do_sqrt != 0: Euclidean) distances.  The m x n matrix is never written.
- * n_neighbors <= 64, k <= 320.  The call synchronises the stream once per database pass.  A slot that
+ * n_neighbors <= 64, k <= 320.  Asynchronous like every other entry point: a pass whose per-row candidate lists overflowed
+ * in a way that matters (database ordered by decreasing distance, ...) is repaired on the device.  A slot that
  * cannot be filled (fewer than n_neighbors comparable rows: NaN distances) holds index -1, distance +inf. */
 size_t b2d_knn_l2_workspace_bytes(int64_t m, int64_t n, int64_t k, int64_t n_neighbors);
 /* the same for metric in {L2Expanded, L2Unexpanded, L2SqrtExpanded, L2SqrtUnexpanded, CosineExpanded,

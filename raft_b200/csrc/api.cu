@@ -1037,7 +1037,8 @@ static size_t knn_topk_offset(int64_t m, int64_t n, int64_t k) { return align_up
 size_t b2d_knn_l2_workspace_bytes(int64_t m, int64_t n, int64_t k, int64_t n_neighbors)
 {
   if (m < 0 || n < 0 || k < 0 || n_neighbors < 1 || n_neighbors > KNN_MAX_K) return static_cast<size_t>(-1);
-  return knn_topk_offset(m, n, k) + align_up(static_cast<size_t>(m) * n_neighbors * 8, 1024);
+  return knn_topk_offset(m, n, k) + align_up(static_cast<size_t>(m) * n_neighbors * 8, 1024) +
+         align_up(static_cast<size_t>(m) * 8, 1024) + align_up(static_cast<size_t>(m) * 4, 1024) + 1024;  // + dropmin, dirty list, counters
 }
 
 namespace {
@@ -1050,14 +1051,19 @@ struct KnnCtx {
   long long* topk;
   float* thr;
   unsigned* cnt;
-  unsigned* overflow;
+  long long* dropmin;   // [m] best key that did not fit into a row's list this pass
+  int* dirty;           // [m] rows to redo for the current pass
+  unsigned* dirty_cnt;  // [64] one counter per pass
+  int pass;
+  const float* x; int64_t ldx;
+  const float* y; int64_t ldy;
+  int family, center;
   int kk;
 };
 }  // namespace
 
-// one pass over y rows [off, off + width): append, then fold into the top-k; a pass whose lists
-// overflowed (more than KNN_CAP entries for some row: ordered / adversarial data) is dropped and
-// repeated as two halves -- a width of KNN_CAP cannot overflow
+// one pass over y rows [off, off + width): append, fold into the top-k, redo the rows whose lists overflowed in a way
+// that matters (knn_merge_kernel / knn_fix_kernel) -- all on the device: the call only enqueues work
 static int knn_pass(KnnCtx& c, int64_t off, int64_t width)
 {
   TcWorkspace w2 = c.w;
@@ -1069,22 +1075,19 @@ static int knn_pass(KnnCtx& c, int64_t off, int64_t width)
   p.idx_offset   = off;
   int rc         = launch_tc(c.s, w2, p, c.k, EPI_TOPK, POST_NONE);
   if (rc) return rc;
-  unsigned of = 0;
-  B2D_CUDA(cudaMemcpyAsync(&of, c.overflow, sizeof(of), cudaMemcpyDeviceToHost, c.s));
-  B2D_CUDA(cudaStreamSynchronize(c.s));
-  const unsigned blocks = static_cast<unsigned>((c.p.m + 255) / 256);
-  if (of != 0u) {
-    if (width <= KNN_CAP) return fail(B2D_ERR_CUDA, "internal: kNN list overflow at minimum pass width");
-    knn_reset_kernel<<<blocks, 256, 0, c.s>>>(c.cnt, c.overflow, c.p.m);
-    B2D_CUDA(cudaGetLastError());
-    const int64_t half = std::max<int64_t>(KNN_CAP, (width / 2 + KNN_CAP - 1) / KNN_CAP * KNN_CAP);
-    rc = knn_pass(c, off, std::min(half, width));
-    if (rc) return rc;
-    if (half < width) rc = knn_pass(c, off + half, width - half);
-    return rc;
-  }
-  knn_merge_kernel<<<static_cast<unsigned>((c.p.m + 7) / 8), 256, 0, c.s>>>(c.topk, c.p.knn_cand, c.cnt, c.thr, c.p.m, c.kk);
+  unsigned* dc = c.dirty_cnt + (c.pass & 63);
+  knn_merge_kernel<<<static_cast<unsigned>((c.p.m + 7) / 8), 256, 0, c.s>>>(c.topk, c.p.knn_cand, c.cnt, c.thr, c.dropmin, c.dirty,
+                                                                            dc, c.p.m, c.kk);
   B2D_CUDA(cudaGetLastError());
+  if (width > KNN_CAP) {  // (a pass of at most KNN_CAP columns cannot overflow)
+    int sms = 0, cc = 0;
+    rc = device_sms(&sms, &cc);
+    if (rc) return rc;
+    knn_fix_kernel<<<sms * 2, 256, 0, c.s>>>(c.topk, c.thr, c.dirty, dc, c.x, c.ldx, c.y, c.ldy, static_cast<int>(c.k), c.kk, off,
+                                             width, c.family, c.center);
+    B2D_CUDA(cudaGetLastError());
+  }
+  ++c.pass;
   return B2D_OK;
 }
 
@@ -1130,16 +1133,25 @@ int b2d_knn(void* stream, int64_t* out_idx, float* out_dist, int metric, const f
   c.topk     = reinterpret_cast<long long*>(static_cast<char*>(workspace) + knn_topk_offset(m, n, k));
   c.thr      = reinterpret_cast<float*>(c.w.aux);          // [m] floats ...
   c.cnt      = reinterpret_cast<unsigned*>(c.w.aux) + m;   // ... and [m] counters share the aux block (8 B per row)
-  c.overflow = c.w.cand_cnt;
+  {
+    char* q     = reinterpret_cast<char*>(c.topk) + align_up(static_cast<size_t>(m) * n_neighbors * 8, 1024);
+    c.dropmin   = reinterpret_cast<long long*>(q);
+    q += align_up(static_cast<size_t>(m) * 8, 1024);
+    c.dirty     = reinterpret_cast<int*>(q);
+    q += align_up(static_cast<size_t>(m) * 4, 1024);
+    c.dirty_cnt = reinterpret_cast<unsigned*>(q);
+  }
+  c.pass = 0; c.x = x; c.ldx = ldx; c.y = y; c.ldy = ldy;
+  c.family = mode == PREP_COSINE ? 1 : 0; c.center = center;
   int rc = launch_prep<float>(s, c.w, x, ldx, 1, m, y, ldy, 1, n, k, nullptr, nullptr, mode, center);
   if (rc) return rc;
   const int64_t total = m * n_neighbors;
-  knn_init_kernel<<<static_cast<unsigned>((std::max<int64_t>(total, m) + 255) / 256), 256, 0, s>>>(c.topk, c.thr, c.cnt, c.overflow, m, c.kk);
+  knn_init_kernel<<<static_cast<unsigned>((std::max<int64_t>(std::max<int64_t>(total, m), 64) + 255) / 256), 256, 0, s>>>(c.topk, c.thr, c.cnt, c.dropmin, c.dirty_cnt, m, c.kk);
   B2D_CUDA(cudaGetLastError());
   memset(&c.p, 0, sizeof(c.p));
   c.p.m = m;
   c.p.knn_thr = c.thr; c.p.knn_cnt = c.cnt; c.p.knn_cand = reinterpret_cast<long long*>(c.w.cand);
-  c.p.knn_cap = KNN_CAP; c.p.knn_overflow = c.overflow;
+  c.p.knn_cap = KNN_CAP; c.p.knn_dropmin = c.dropmin;
   // pass widths KNN_CAP, KNN_CAP, 2 KNN_CAP, 4 KNN_CAP, ...: with the k-th best of the s columns seen so far as
   // threshold, a pass over the next s columns appends ~n_neighbors entries per row on unordered data
   int64_t off = 0;

@@ -112,7 +112,8 @@ struct TcParams {
   unsigned* knn_cnt;      // [m] fill counter of the row's candidate list
   long long* knn_cand;    // [m][knn_cap] packed (ordered bits of the distance << 32 | index)
   unsigned knn_cap;
-  unsigned* knn_overflow; // [1] set when a row's list is full (the pass is then repeated in halves)
+  long long* knn_dropmin; // [m] smallest key that did not fit into the row's list this pass (knn_merge_kernel decides whether
+                          //     anything that matters was lost; rows where it was are redone by knn_fix_kernel)
 };
 
 constexpr size_t TC_SMEM_OPERANDS = (size_t)TC_MAX_RES_KB * TC_B_BYTES + (size_t)TC_STAGES_RES * TC_A_BYTES;  // 224 KB
@@ -790,8 +791,8 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                           if (slot < p.knn_cap)
                             p.knn_cand[row * p.knn_cap + slot] =
                               (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
-                          else
-                            *p.knn_overflow = 1u;
+                          else  // list full (ordered / adversarial data): remember the best key that was dropped
+                            atomicMin(&p.knn_dropmin[row], (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll));
                         }
                       }
                   }
@@ -984,31 +985,27 @@ constexpr int KNN_MAX_K = 64;
 constexpr int KNN_CAP   = 128;   // list entries per row and pass
 constexpr int KNN_SORT  = 256;   // KNN_MAX_K + KNN_CAP padded to a power of two
 
-__global__ void knn_init_kernel(long long* topk, float* thr, unsigned* cnt, unsigned* overflow, int64_t m, int kk)
+__global__ void knn_init_kernel(long long* topk, float* thr, unsigned* cnt, long long* dropmin, unsigned* dirty_cnt, int64_t m,
+                                int kk)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i == 0) *overflow = 0u;
-  if (i < m) { thr[i] = __int_as_float(0x7f800000); cnt[i] = 0u; }
+  if (i < 64) dirty_cnt[i] = 0u;   // one counter per pass
+  if (i < m) { thr[i] = __int_as_float(0x7f800000); cnt[i] = 0u; dropmin[i] = 0x7FFFFFFFFFFFFFFFll; }
   if (i < m * kk) topk[i] = 0x7FFFFFFFFFFFFFFFll;
 }
 
-// drop the lists of a pass that overflowed (it is repeated in halves)
-__global__ void knn_reset_kernel(unsigned* cnt, unsigned* overflow, int64_t m)
-{
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i == 0) *overflow = 0u;
-  if (i < m) cnt[i] = 0u;
-}
-
-// one warp per row: sort (top-k so far) + (this pass's list) by (distance, index), keep the first kk
+// one warp per row: sort (top-k so far) + (this pass's list) by (distance, index), keep the first kk.  A row whose list
+// was full lost entries; that only matters if the best dropped key could still enter the new top-k -- such rows go
+// to the pass's dirty list and knn_fix_kernel redoes them over the pass's columns (no host round trip anywhere).
 __global__ void __launch_bounds__(256) knn_merge_kernel(long long* topk, const long long* cand, unsigned* cnt, float* thr,
-                                                        int64_t m, int kk)
+                                                        long long* dropmin, int* dirty, unsigned* dirty_cnt, int64_t m, int kk)
 {
   __shared__ long long buf[8][KNN_SORT];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + wid;
   if (row >= m) return;
-  const unsigned nc = min(cnt[row], static_cast<unsigned>(KNN_CAP));
+  const unsigned craw = cnt[row];
+  const unsigned nc   = min(craw, static_cast<unsigned>(KNN_CAP));
   if (nc == 0u) return;  // nothing new for this row (the common case in the late passes)
   long long* b = buf[wid];
   for (int t = lane; t < KNN_SORT; t += 32) {
@@ -1035,6 +1032,112 @@ __global__ void __launch_bounds__(256) knn_merge_kernel(long long* topk, const l
     if (kth != 0x7FFFFFFFFFFFFFFFll) {
       const int sb = static_cast<int>(kth >> 32);
       thr[row]     = __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
+    }
+    if (craw > static_cast<unsigned>(KNN_CAP)) {
+      if (dropmin[row] <= kth) dirty[atomicAdd(dirty_cnt, 1u)] = static_cast<int>(row);
+      dropmin[row] = 0x7FFFFFFFFFFFFFFFll;
+    }
+  }
+}
+
+// Rows whose candidate list overflowed in a way that matters (database ordered by decreasing distance, duplicates of one
+// near point, ...): one block per dirty row re-evaluates the pass's columns [off, off + width) straight from the fp32
+// inputs -- family 0: sum (x - y)^2, family 1: 1 - <x', y'> / (|x'||y'|) with x' centred for correlation -- one column per
+// thread, and folds them into the row's top-k (entries this pass had already contributed are taken out first, so no
+// column can appear twice).  Exact for any input order; costs O(width * k) per dirty row, nothing when the list is empty.
+__global__ void __launch_bounds__(256) knn_fix_kernel(long long* topk, float* thr, const int* dirty, const unsigned* dirty_cnt,
+                                                      const float* x, int64_t ldx, const float* y, int64_t ldy, int k, int kk,
+                                                      int64_t off, int64_t width, int family, int center)
+{
+  __shared__ float xs[320];
+  __shared__ long long keys[512];
+  __shared__ unsigned ncand;
+  __shared__ float xstat[2];
+  const int tid = threadIdx.x;
+  const unsigned total = *dirty_cnt;
+  for (unsigned d = blockIdx.x; d < total; d += gridDim.x) {
+    const int64_t row = dirty[d];
+    __syncthreads();
+    if (tid == 0) {
+      float mean = 0.f;
+      if (family == 1 && center) {
+        for (int t = 0; t < k; ++t) mean += x[row * ldx + t];
+        mean /= static_cast<float>(k);
+      }
+      float nx = 0.f;
+      for (int t = 0; t < k; ++t) { const float v = x[row * ldx + t] - mean; nx = fmaf(v, v, nx); }
+      xstat[0] = mean; xstat[1] = nx;
+    }
+    __syncthreads();
+    for (int t = tid; t < k; t += 256) xs[t] = x[row * ldx + t] - xstat[0];
+    // the row's top-k without what this pass had put in
+    for (int t = tid; t < 512; t += 256) {
+      long long key = 0x7FFFFFFFFFFFFFFFll;
+      if (t < kk) {
+        key = topk[row * kk + t];
+        const long long j = key & 0xFFFFFFFFll;
+        if (key != 0x7FFFFFFFFFFFFFFFll && j >= off && j < off + width) key = 0x7FFFFFFFFFFFFFFFll;
+      }
+      keys[t] = key;
+    }
+    if (tid == 0) ncand = 0u;
+    __syncthreads();
+    for (int64_t j0 = 0; j0 < width; j0 += 256) {
+      // (the k-th best of what is in keys[0, kk) bounds what can still enter; unsorted holes are +max)
+      long long kth = 0;
+      for (int t = 0; t < kk; ++t) kth = max(kth, keys[t]);
+      const int64_t j = j0 + tid;
+      if (j < width) {
+        const float* yr = y + (off + j) * ldy;
+        float val;
+        if (family == 0) {
+          float acc = 0.f;
+          for (int t = 0; t < k; ++t) { const float df = xs[t] - __ldg(yr + t); acc = fmaf(df, df, acc); }
+          val = acc;
+        } else {
+          float my = 0.f;
+          if (center) {
+            for (int t = 0; t < k; ++t) my += __ldg(yr + t);
+            my /= static_cast<float>(k);
+          }
+          float dot = 0.f, ny = 0.f;
+          for (int t = 0; t < k; ++t) { const float b = __ldg(yr + t) - my; dot = fmaf(xs[t], b, dot); ny = fmaf(b, b, ny); }
+          val = 1.f - dot / sqrtf(xstat[1] * ny);
+        }
+        const long long key = (static_cast<long long>(ordered_bits(val)) << 32) | ((off + j) & 0xFFFFFFFFll);
+        if (key < kth && val == val) keys[kk + atomicAdd(&ncand, 1u)] = key;   // (kk + 256 <= 320 < 512)
+      }
+      __syncthreads();
+      if (ncand != 0u) {   // block-wide bitonic sort of the 512 slots, smallest first
+        for (int size = 2; size <= 512; size <<= 1)
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int t = tid;
+            const int i = 2 * t - (t & (stride - 1)), jj = i + stride;
+            const bool up = (i & size) == 0;
+            const long long a = keys[i], c = keys[jj];
+            if ((a > c) == up) { keys[i] = c; keys[jj] = a; }
+            __syncthreads();
+          }
+        for (int t = kk + tid; t < 512; t += 256) keys[t] = 0x7FFFFFFFFFFFFFFFll;
+        if (tid == 0) ncand = 0u;
+        __syncthreads();
+      }
+    }
+    // final order (holes from the removed entries may have left the first kk slots unsorted)
+    for (int size = 2; size <= 512; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const int t = tid;
+        const int i = 2 * t - (t & (stride - 1)), jj = i + stride;
+        const bool up = (i & size) == 0;
+        const long long a = keys[i], c = keys[jj];
+        if ((a > c) == up) { keys[i] = c; keys[jj] = a; }
+        __syncthreads();
+      }
+    for (int t = tid; t < kk; t += 256) topk[row * kk + t] = keys[t];
+    if (tid == 0) {
+      const long long kth = keys[kk - 1];
+      const int sb        = static_cast<int>(kth >> 32);
+      thr[row] = kth == 0x7FFFFFFFFFFFFFFFll ? __int_as_float(0x7f800000) : __int_as_float(sb < 0 ? (sb ^ 0x7FFFFFFF) : sb);
     }
   }
 }

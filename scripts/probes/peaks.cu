@@ -21,14 +21,22 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64
 // kind::tf32 instruction descriptor: D = f32 (1 << 4), A = B = tf32 (format 2 at bits [7,10) and [10,13))
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24); }
 
-template <int kKind, int kN>   // kKind 0: f16, 1: tf32
+template <int kKind, int kN, int kData>   // kKind 0: f16, 1: tf32; kData 1: random operands, 0: constant
 __global__ void __launch_bounds__(128, 1) mma_peak(int iters)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 ones / small tf32
+  // operands: pseudo-random finite values (constant operands barely toggle the datapath: the first version of this probe
+  // ran at 2235 TF/s WITHOUT ever reaching the power cap); kData = 0 keeps the constant fill for comparison
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) {
+    uint32_t h = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    // two fp16 in [-2, 2): sign + exponent 0x3c00 +- 1 + random mantissa  (as tf32 bits: a finite value of modest size as well)
+    const uint32_t lo = (h & 0x83ffu) | 0x3c00u, hi = ((h >> 16) & 0x83ffu) | 0x3800u;
+    reinterpret_cast<uint32_t*>(smem)[i] = kData ? (lo | (hi << 16)) : 0x3c003c00u;
+  }
   if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
   if (warp == 0) ptx::tmem_alloc<512>(&slot);
   ptx::fence_proxy_async_smem();
@@ -112,15 +120,18 @@ int main()
   printf("%s, %d SMs, max SM clock %d MHz\n", prop.name, sms, prop.clockRate / 1000);
   const int iters = 20000;
   const size_t smem = 16384 + 32768 + 1024;
-  cudaFuncSetAttribute(mma_peak<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(mma_peak<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(mma_peak<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  run("tcgen05.mma kind::f16 M128 N256 K16 (TFLOP/s)", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 256 * 16, "TF/s",
-      [&] { mma_peak<0, 256><<<sms, 128, smem>>>(iters); });
-  run("tcgen05.mma kind::f16 M128 N128 K16 (TFLOP/s)", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 128 * 16, "TF/s",
-      [&] { mma_peak<0, 128><<<sms, 128, smem>>>(iters); });
-  run("tcgen05.mma kind::tf32 M128 N256 K8 (TFLOP/s)", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 256 * 8, "TF/s",
-      [&] { mma_peak<1, 256><<<sms, 128, smem>>>(iters); });
+  cudaFuncSetAttribute(mma_peak<0, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(mma_peak<0, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(mma_peak<0, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(mma_peak<1, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  run("tcgen05.mma kind::f16 M128 N256 K16, random data", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 256 * 16, "TF/s",
+      [&] { mma_peak<0, 256, 1><<<sms, 128, smem>>>(iters); });
+  run("tcgen05.mma kind::f16 M128 N256 K16, constant data", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 256 * 16, "TF/s",
+      [&] { mma_peak<0, 256, 0><<<sms, 128, smem>>>(iters); });
+  run("tcgen05.mma kind::f16 M128 N128 K16, random data", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 128 * 16, "TF/s",
+      [&] { mma_peak<0, 128, 1><<<sms, 128, smem>>>(iters); });
+  run("tcgen05.mma kind::tf32 M128 N256 K8, random data", 1.0 * sms * (double)iters * 8 * 2.0 * 128 * 256 * 8, "TF/s",
+      [&] { mma_peak<1, 256, 1><<<sms, 128, smem>>>(iters); });
   float* out; cudaMalloc(&out, 4);
   const int fi = 200000;
   run("FP32 pipe FFMA (lane-ops/s, 1 FFMA = 1 lane-op)", 1.0 * sms * 1024.0 * fi * 8, "Tlop/s",
