@@ -263,7 +263,7 @@ def silhouette_score(x, labels, n_labels=None, metric=None, metric_arg=2.0, retu
 def trustworthiness_score(x, x_embedded, n_neighbors: int = 5, metric=None):
     """Restates raft::stats::trustworthiness_score (cpp/include/raft/stats/detail/
     trustworthiness_score.cuh:113-211): neighbours j of i in the embedded space (n_neighbors + 1 with i
-    itself, Euclidean), r(i, j) = position of j in the order of the samples by original-space distance
+    itself, in the caller's metric), r(i, j) = position of j in the order of the samples by original-space distance
     from i (i first; ties by index), penalty max(0, r - n_neighbors).  Same value as
     sklearn.manifold.trustworthiness."""
     metric = DistanceType.L2SqrtUnexpanded if metric is None else metric
@@ -275,7 +275,13 @@ def trustworthiness_score(x, x_embedded, n_neighbors: int = 5, metric=None):
     order = np.lexsort((np.broadcast_to(np.arange(n), d.shape), d), axis=1)
     rank = np.empty_like(order)
     np.put_along_axis(rank, order, np.broadcast_to(np.arange(n), d.shape), axis=1)
-    nbr, _ = knn_l2(e, e, k + 1)
+    if metric in (DistanceType.L2SqrtUnexpanded, DistanceType.L2Unexpanded, DistanceType.L2Expanded,
+                  DistanceType.L2SqrtExpanded):
+        nbr, _ = knn_l2(e, e, k + 1)
+    else:   # run_knn<distance_type> (trustworthiness_score.cuh:79-104): the SAME metric in the embedded space
+        de = pairwise_distance(e, e, metric, 2.0)
+        np.fill_diagonal(de, -np.inf)
+        nbr = np.lexsort((np.broadcast_to(np.arange(n), de.shape), de), axis=1)[:, :k + 1]
     t = 0.0
     for i in range(n):
         for j in nbr[i]:

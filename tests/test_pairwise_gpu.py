@@ -388,3 +388,18 @@ def test_fp64_fortran_order_and_kl_roles():
     for metric in (DT.KLDivergence, DT.L2Expanded, DT.CosineExpanded):
         got = pairwise_distance(af, bf, metric=metric).copy_to_host()
         assert np.allclose(got, oracle.pairwise_distance(a, b, metric), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("metric", [DT.L2Expanded, DT.L2SqrtExpanded, DT.CosineExpanded, DT.L1])
+def test_nan_rows_propagate_and_stay_local(metric):
+    """A NaN in an input row poisons exactly that row's / column's distances (the finalisation clamp must not turn
+    NaN into 0: fmaxf(NaN, 0) = 0), every other pair keeps the 1e-4 bar."""
+    x, y = blobs(300, 260, 96)
+    x[7, 13] = np.nan
+    y[201, 95] = np.nan
+    got = run(x, y, metric)
+    assert np.isnan(got[7]).all() and np.isnan(got[:, 201]).all()
+    keep_r, keep_c = np.arange(300) != 7, np.arange(260) != 201
+    sub = got[keep_r][:, keep_c]
+    assert np.isfinite(sub).all()
+    check(sub, oracle.pairwise_distance(x[keep_r], y[keep_c], metric))

@@ -81,6 +81,20 @@ def test_trustworthiness_vs_oracle(shape, quality):
     assert trustworthiness_score(xt, xt, n_neighbors=k) == 1.0
 
 
+def test_trustworthiness_uses_the_callers_metric_in_both_spaces():
+    """Cosine neighbourhoods differ from L2 ones when the rows have different lengths: the embedded-space kNN must use
+    the metric the caller names (round 1 hard-wired L2 there)."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((600, 24)).astype(np.float32) * rng.uniform(0.1, 10, (600, 1)).astype(np.float32)
+    e = (x @ rng.standard_normal((24, 4)).astype(np.float32)).astype(np.float32)
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda()
+    ref_cos = oracle.trustworthiness_score(x, e, 7, metric=oracle.DistanceType.CosineExpanded)
+    ref_l2 = oracle.trustworthiness_score(x, e, 7)
+    assert abs(ref_cos - ref_l2) > 1e-3                      # the two definitions are told apart by this data
+    assert abs(trustworthiness_score(xt, et, n_neighbors=7, metric="cosine") - ref_cos) < 1e-4
+    assert abs(trustworthiness_score(xt, et, n_neighbors=7) - ref_l2) < 1e-4
+
+
 def test_trustworthiness_argument_errors():
     x = torch.randn(50, 6, device="cuda")
     with pytest.raises(LogicError):
