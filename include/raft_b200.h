@@ -90,9 +90,9 @@ int b2d_version(void);
  *   "nn_tau"     candidates per row above which the trial pass calls screening off (default 6) */
 int b2d_set_option(const char* name, double value);
 /* Diagnostic -- SYNCHRONISES `stream`: control words of the last screened fusedL2NN chunk in `workspace`:
- * [0] candidates incl. one incumbent per row, [1] list overflow, [2] go_screen, [3] go_exact, [4] redo_trial,
- * [5] candidates after the trial pass. */
-int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out6);
+ * [0] list slots in use (one incumbent per row + the blocks of 64 the screen reserved), [1] list overflow, [2] go_screen,
+ * [3] go_exact, [4] redo_trial, [5] candidates after the trial pass, [6] candidates found by the screen.  `out7`: 7 words. */
+int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out7);
 /* thread-local description of the last non-zero status returned on this thread */
 const char* b2d_last_error(void);
 

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/raft_b200.h"
 #include "expanded_tc.cuh"
@@ -141,8 +142,14 @@ struct TcWorkspace {
   int2* cand;        // [cap]  screened NN: candidate list
   unsigned* cand_cnt;  // [1] (+ overflow flag right behind it)
   unsigned cand_cap;
+  // screened NN: the database chunk is worked through in the order of its squared row norms (screen_tc.cuh)
+  unsigned* sort_key[2];  // [min(n, 2^20)] each
+  int* sort_val[2];       // [min(n, 2^20)] each: position -> source row
+  void* sort_tmp;
   size_t bytes;
 };
+constexpr int64_t kNnChunkRows  = 1 << 20;   // database rows per screened chunk
+constexpr size_t kSortTmpBytes  = 4u << 20;  // cub::DeviceRadixSort scratch for <= 2^20 pairs (checked at run time)
 
 static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool with_keys)
 {
@@ -167,7 +174,9 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   // screened fusedL2NN scratch: thresholds, counters, candidate list (128 per row and 1M-row chunk of y;
   // ~54 measured on far-from-origin clusters; overflow falls back to the exact pass on the device,
   // never to a wrong answer)
-  w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(128 * m + (1 << 16), 0x7fffffff)) : 0u;
+  // (+2^19: the coarse kernel's warps take list slots in blocks of 64 -- 148 x 16 warps x 2 launches leave up to
+  // ~300k slots unused, which must not look like an overflow when m is small)
+  w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(128 * m + (1 << 19), 0x7fffffff)) : 0u;
   w.aux      = reinterpret_cast<float2*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
   w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 32 : 0));
   w.cand     = reinterpret_cast<int2*>(c + take(static_cast<size_t>(w.cand_cap) * 8));
@@ -175,6 +184,12 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   w.ysc  = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
   w.xop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(m) * nkb * 128));
   w.yop  = reinterpret_cast<__half*>(c + take(static_cast<size_t>(n) * nkb * 128));
+  const size_t ns = with_keys ? static_cast<size_t>(std::min<int64_t>(n, kNnChunkRows)) : 0;
+  for (int i = 0; i < 2; ++i) {
+    w.sort_key[i] = reinterpret_cast<unsigned*>(c + take(ns * 4));
+    w.sort_val[i] = reinterpret_cast<int*>(c + take(ns * 4));
+  }
+  w.sort_tmp = c + take(with_keys ? kSortTmpBytes : 0);
   w.bytes = off;
   return w;
 }
@@ -196,11 +211,12 @@ static bool is_unexpanded(int metric)
 template <typename T>
 static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int64_t xrs, int64_t xcs, int64_t m,
                        const void* y, int64_t yrs, int64_t ycs, int64_t n, int64_t k, const float* xn, const float* yn,
-                       int mode, int center, int xform = 0, float coef_mul = 1.f, float tx_const = 0.f)
+                       int mode, int center, int xform = 0, float coef_mul = 1.f, float tx_const = 0.f,
+                       const int* y_gather = nullptr)
 {
   PrepParams p;
-  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, w.xsc, xn};
-  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, w.ysc, yn};
+  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, w.xsc, xn, nullptr};
+  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, w.ysc, yn, y_gather};
   p.k = static_cast<int>(k); p.nkb = static_cast<int>((k + 31) / 32); p.mode = mode; p.center = center;
   p.gmax = w.gmax; p.coef = w.coef; p.has_lo = w.has_lo; p.nonuni = w.nonuni;
   p.xform = xform; p.coef_mul = coef_mul; p.tx_const = tx_const;
@@ -376,7 +392,7 @@ static int launch_tc(cudaStream_t s, const TcWorkspace& w, TcParams p, int64_t k
 // coarse screening pass of the screened fusedL2NN (screen_tc.cuh) over the y blocks with
 // sel_lo <= index % sel_s < sel_hi
 static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_t n, int64_t k, int sel_s, int sel_lo,
-                         int sel_hi, unsigned* overflow, const unsigned* run_flag, int unit_norm)
+                         int sel_hi, unsigned* overflow, const unsigned* run_flag, int unit_norm, const int* col_map)
 {
   int sms = 0, cc = 0;
   int rc  = device_sms(&sms, &cc);
@@ -402,7 +418,7 @@ static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_
   p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
   p.xsc = w.xsc; p.nonuni = w.nonuni;
   p.yt = w.yt; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
-  p.overflow = overflow; p.run_flag = run_flag; p.unit_norm = unit_norm;
+  p.overflow = overflow; p.run_flag = run_flag; p.unit_norm = unit_norm; p.col_map = col_map;
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb;
   rc = make_operand_map(&ma, w.xop, m, p.nkb, TC_BM, 0, 0, true);
@@ -634,16 +650,25 @@ int b2d_set_option(const char* name, double value)
 }
 
 // Diagnostic (synchronises `stream`): the control words the last screened fusedL2NN chunk left in `workspace`
-// [0] candidates (incl. one incumbent per row) [1] list overflow [2] go_screen [3] go_exact [4] redo_trial [5] candidates after the trial
-int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out6)
+// [0] list slots in use (one incumbent per row + blocks of 64 reserved by the screen) [1] list overflow [2] go_screen [3] go_exact [4] redo_trial [5] candidates after the trial [6] candidates found by the screen (out7: 7 words)
+int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out6 /* 7 words */)
 {
   if (!workspace || !out6 || m < 0 || n < 0 || k < 0) return fail(B2D_ERR_INVALID_ARG, "null workspace / out");
   TcWorkspace w = tc_layout(const_cast<void*>(workspace), m, n, k, true);
   B2D_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-  B2D_CUDA(cudaMemcpy(out6, w.cand_cnt, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  B2D_CUDA(cudaMemcpy(out6, w.cand_cnt, 7 * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return B2D_OK;
 }
 const char* b2d_last_error(void) { return g_err.c_str(); }
+#ifdef SC_TRACE
+int b2d_debug_screen_trace(long long* out_host)
+{
+  B2D_CUDA(cudaDeviceSynchronize());
+  B2D_CUDA(cudaMemcpyFromSymbol(out_host, g_sc_trace, sizeof(long long) * 8 * 4096));
+  B2D_CUDA(cudaMemcpyFromSymbol(out_host + 8 * 4096, g_sc_wtrace, sizeof(long long) * 3 * 16 * 2048));
+  return B2D_OK;
+}
+#endif
 
 size_t b2d_pairwise_workspace_bytes(int metric, int dtype, int64_t m, int64_t n, int64_t k)
 {
@@ -778,16 +803,35 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
                                void* workspace, int mode, int center, bool allow_screen)
 {
   TcWorkspace w = tc_layout(workspace, m, n, k, true);
-  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, mode, center);
+  const int nkb = static_cast<int>((k + 31) / 32);
+  // (k <= 64: the exact kernel is already epilogue-bound, screening would not pay)
+  const bool screen = (mode == PREP_L2 || mode == PREP_COSINE) && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && allow_screen;
+  const int unit_norm = mode == PREP_COSINE ? 1 : 0;
+  // The coarse pass bounds a whole 32-column group at once: c * max_j(acc_ij) + min_j |y_j|^2 (screen_tc.cuh).  That is
+  // only tight when the rows of a group have nearly equal norms, so the L2 search packs the chunk in the order of
+  // its squared row norms (stable radix sort on the top 24 bits of the fp32 norm: deterministic); the kernels
+  // translate a packed position back to the source row where an index leaves them (col_map).  The cosine family
+  // needs none of this: its column term is the constant 0.
+  const int* col_map = nullptr;
+  if (screen && !unit_norm && n > 0) {
+    if (n > kNnChunkRows) return fail(B2D_ERR_INVALID_ARG, "internal: screened chunk larger than 2^20 rows");
+    nn_sortkey_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(y, ldy, n, static_cast<int>(k), yn, w.sort_key[0], w.sort_val[0]);
+    B2D_CUDA(cudaGetLastError());
+    cub::DoubleBuffer<unsigned> dk(w.sort_key[0], w.sort_key[1]);
+    cub::DoubleBuffer<int> dv(w.sort_val[0], w.sort_val[1]);
+    size_t tmp_need = 0;
+    B2D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_need, dk, dv, static_cast<int>(n), 8, 32, s));
+    if (tmp_need > kSortTmpBytes) return fail(B2D_ERR_WORKSPACE, "internal: radix sort scratch " + std::to_string(tmp_need) + " bytes");
+    B2D_CUDA(cub::DeviceRadixSort::SortPairs(w.sort_tmp, tmp_need, dk, dv, static_cast<int>(n), 8, 32, s));
+    col_map = dv.Current();
+  }
+  int rc = launch_prep<float>(s, w, x, ldx, 1, m, y, ldy, 1, n, k, xn, yn, mode, center, 0, 1.f, 0.f, col_map);
   if (rc) return rc;
   if (n == 0) return B2D_OK;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.m = m; p.n = n; p.keys = reinterpret_cast<long long*>(keys); p.idx_offset = idx_offset;
-  const int nkb = static_cast<int>((k + 31) / 32);
-  // (k <= 64: the exact kernel is already epilogue-bound, screening would not pay)
-  const bool screen = (mode == PREP_L2 || mode == PREP_COSINE) && nkb >= 3 && nkb <= TC_MAX_RES_KB && n >= 16384 && allow_screen;
-  const int unit_norm = mode == PREP_COSINE ? 1 : 0;
+  p.col_map = col_map;
   if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 
   // Screened search (screen_tc.cuh).  With S = 32 and r = index of a 256-row y block modulo S:
@@ -810,11 +854,11 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
                                                                          w.cand, flags, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr, unit_norm);
+  rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr, unit_norm, col_map);
   if (rc) return rc;
   nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 1, w.nonuni);
   B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2, unit_norm);
+  rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2, unit_norm, col_map);
   if (rc) return rc;
   nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 2, w.nonuni);
   B2D_CUDA(cudaGetLastError());
@@ -822,7 +866,7 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   rc = device_sms(&sms, &cc);
   if (rc) return rc;
   nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
-                                          ldy, static_cast<int>(k), idx_offset, unit_norm, center);
+                                          ldy, static_cast<int>(k), idx_offset, unit_norm, center, static_cast<unsigned>(m), col_map);
   B2D_CUDA(cudaGetLastError());
   p.sel_lo = 1; p.sel_hi = 2; p.run_flag = flags + 4;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
@@ -857,7 +901,7 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   // chunk, and every chunk starts from the bounds the earlier ones left in the keys.
   const int nkb_all    = static_cast<int>((k + 31) / 32);
   const bool screen_ok = (mode == PREP_L2 || mode == PREP_COSINE) && nkb_all >= 3 && nkb_all <= TC_MAX_RES_KB && !screen_off;
-  constexpr int64_t kChunkRows = 1 << 20;
+  constexpr int64_t kChunkRows = kNnChunkRows;
   if (!screen_ok || n <= kChunkRows)
     return fused_nn_keys_chunk(s, keys, x, ldx, y, ldy, xn, yn, m, n, k, idx_offset, workspace, mode, center, screen_ok);
   for (int64_t off = 0; off < n; off += kChunkRows) {

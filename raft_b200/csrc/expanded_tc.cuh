@@ -106,6 +106,7 @@ struct TcParams {
   // EPI_MINLOC
   long long* keys;        // [m] packed (ordered bits of the distance << 32 | index)
   int64_t idx_offset;
+  const int* col_map;     // non-null: column j of the packed y is source row col_map[j] (norm-sorted chunk, api.cu)
   const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
   // EPI_TOPK (fused brute-force kNN): every pair at or below the row's current k-th best joins the row's list
   const float* knn_thr;   // [m] current k-th best squared distance of the row (+inf until k are known)
@@ -183,6 +184,13 @@ __device__ __forceinline__ float min3(float a, float b, float c)
 {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
 
@@ -772,7 +780,18 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                       if (v[4 * i + o] == mn) cbest = 8 * i;
                     }
                     const float dv      = mn + xnr[j];
-                    const long long gj  = static_cast<long long>(n_blk) * TC_BN + cl0 + cbest + p.idx_offset;
+                    long long gj        = static_cast<long long>(n_blk) * TC_BN + cl0 + cbest;
+                    if (p.col_map != nullptr) {  // permuted columns: the smallest SOURCE index among the equal minima
+                      int best = 0x7fffffff;
+#pragma unroll
+                      for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                          if (v[4 * i + o + e] == mn)
+                            best = min(best, __ldg(&p.col_map[static_cast<int64_t>(n_blk) * TC_BN + cl0 + 8 * i + e]));
+                      gj = best;
+                    }
+                    gj += p.idx_offset;
                     const long long key = (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
                     atomicMin(&p.keys[row0 + 8 * j], key);
                     thr[j] = dv;
@@ -865,14 +884,36 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, int64_
 // re-evaluated exactly, straight from the fp32 inputs (sum (x-y)^2), together with the incumbent,
 // so every finalist is measured with the same arithmetic.
 
+// sort key of a database row: the bits of its squared norm (fp32, non-negative: the unsigned order is the float order)
+__global__ void __launch_bounds__(256) nn_sortkey_kernel(const float* y, int64_t ldy, int64_t n, int k, const float* yn,
+                                                         unsigned* key, int* val)
+{
+  const int lane  = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  float ss = 0.f;
+  if (yn != nullptr) {
+    ss = __ldg(&yn[r]);
+  } else {
+    const float* row = y + r * ldy;
+    for (int t = lane; t < k; t += 32) { const float v = __ldg(row + t); ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) {
+    key[r] = (ss >= 0.f) ? __float_as_uint(ss) : 0xffffffffu;   // NaN / negative caller norms: last
+    val[r] = static_cast<int>(r);
+  }
+}
+
 // after the exact sub-sampled pass: thr = incumbent distance, incumbent -> candidate, keys reset
 __global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, int2* cand, unsigned* flags,
                                int64_t m, int64_t n, int64_t idx_offset)
 {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i == 0) {  // [0] candidate count [1] overflow [2] go_screen [3] go_exact [4] redo_trial [5] count after the trial
-    flags[0] = static_cast<unsigned>(m);
-    flags[1] = flags[2] = flags[3] = flags[4] = flags[5] = 0u;
+  if (i == 0) {  // [0] list slots in use [1] overflow [2] go_screen [3] go_exact [4] redo_trial [5] candidates after the trial
+    flags[0] = static_cast<unsigned>(m);   // [6] candidates found by the screen (slots are reserved in blocks)
+    flags[1] = flags[2] = flags[3] = flags[4] = flags[5] = flags[6] = 0u;
   }
   if (i >= m) return;
   const long long key = keys[i];
@@ -899,11 +940,11 @@ __global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, in
 __global__ void nn_decide_kernel(unsigned* flags, unsigned m, float tau, int stage, const unsigned* nonuni)
 {
   if (stage == 1) {
-    flags[5]            = flags[0];
+    flags[5]            = flags[6];
     // per-column scales (rows of y with their own exponent): the screen's single coefficient does not hold ->
     // everything it covered is redone by the exact kernel
     const unsigned redo = (flags[1] != 0u || nonuni[1] != 0u) ? 1u : 0u;
-    const bool many     = static_cast<float>(flags[0] - m) > tau * static_cast<float>(m);
+    const bool many     = static_cast<float>(flags[6]) > tau * static_cast<float>(m);
     flags[4]            = redo;
     flags[3]            = (redo || many) ? 1u : 0u;
     flags[2]            = flags[3] ? 0u : 1u;
@@ -918,14 +959,18 @@ __global__ void nn_decide_kernel(unsigned* flags, unsigned m, float tau, int sta
 // (k <= 128 on this path: a lane holds at most 4 elements of each row in registers)
 __global__ void __launch_bounds__(256) nn_exact_kernel(long long* keys, const int2* cand, const unsigned* cnt,
                                                        unsigned cap, const float* x, int64_t ldx, const float* y,
-                                                       int64_t ldy, int k, int64_t idx_offset, int family, int center)
+                                                       int64_t ldy, int k, int64_t idx_offset, int family, int center,
+                                                       unsigned n_seed, const int* col_map)
 {
   const int lane       = threadIdx.x & 31;
   const unsigned total = min(*cnt, cap);
   const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
   for (unsigned c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < total; c += nwarp) {
-    const int2 ij = cand[c];
+    int2 ij = cand[c];
     if (ij.x < 0) continue;
+    // the first n_seed entries (nn_seed_kernel: the incumbents) hold source rows of y, the screen's entries packed
+    // positions of the norm-sorted chunk
+    if (c >= n_seed && col_map != nullptr) ij.y = __ldg(&col_map[ij.y]);
     const float* xr = x + static_cast<int64_t>(ij.x) * ldx;
     const float* yr = y + static_cast<int64_t>(ij.y) * ldy;
     float xv[4], yv[4];

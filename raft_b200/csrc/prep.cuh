@@ -40,6 +40,7 @@ struct PrepSide {
   float* tvec;      // [rows]
   float* svec;      // [rows] 2^(E - e_row): 1 for every row that shares the matrix exponent E (see prep_split_kernel)
   const float* ext_norm_sq;  // optional caller-provided squared norms (fusedL2NN xn/yn)
+  const int* gather;         // optional: packed row r is source row gather[r] (norm-sorted database of the screened NN search)
 };
 
 struct PrepParams {
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   if (which) r -= p.side[0].rows;
   const PrepSide& sd = p.side[which];
   if (r >= sd.rows) return;
-  const T* row = static_cast<const T*>(sd.src) + r * sd.rs;
+  const int64_t rsrc = sd.gather ? static_cast<int64_t>(__ldg(&sd.gather[r])) : r;  // packed row r <- source row rsrc
+  const T* row = static_cast<const T*>(sd.src) + rsrc * sd.rs;
 
   const int ex = scale_exponent(__uint_as_float(p.gmax[0]));
   const int ey = scale_exponent(__uint_as_float(p.gmax[1]));
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   // epilogue multiplies its products by 2^(E - e_row) (exact: a power of two).  Ordinary data never takes this
   // branch: svec == 1 everywhere and the results are bit-identical to the single-scale scheme.
   const int E      = which ? ey : ex;
-  const double nrm = p.mode == PREP_COSINE ? (sd.ext_norm_sq ? sqrt(static_cast<double>(sd.ext_norm_sq[r])) : sqrt(ss)) : 1.0;
+  const double nrm = p.mode == PREP_COSINE ? (sd.ext_norm_sq ? sqrt(static_cast<double>(sd.ext_norm_sq[rsrc])) : sqrt(ss)) : 1.0;
   const float aeff = p.mode == PREP_COSINE ? (nrm > 0.0 ? static_cast<float>(static_cast<double>(amax) / nrm) : 0.f) : amax;
   int e_row        = E;
   if (aeff > 0.f && aeff < 3.0e38f && ldexpf(aeff, E) < 8.0f) {
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
     atomicExch(p.has_lo, 1u);
   if (lane == 0) {
     float t;
-    if (p.mode == PREP_L2 || p.mode == PREP_INNER_NORM) t = sd.ext_norm_sq ? sd.ext_norm_sq[r] : static_cast<float>(ss);
+    if (p.mode == PREP_L2 || p.mode == PREP_INNER_NORM) t = sd.ext_norm_sq ? sd.ext_norm_sq[rsrc] : static_cast<float>(ss);
     else if (p.mode == PREP_COSINE) t = which == 0 ? 1.f : 0.f;
     else t = which == 0 ? p.tx_const : 0.f;
     sd.tvec[r] = t;

@@ -10,8 +10,12 @@
 // factor 2; the remaining 5% of the margin and the 2^-21 |y|^2 cover the fp32 rounding of the
 // epilogue).  Only pairs with L_ij <= U_i can hold the minimum: they go to a candidate list that
 // nn_exact_kernel re-measures straight from the fp32 inputs.  The margin is a per-row constant
-// inside a y block, so it moves into the row's threshold and the element loop is one FFMA2 plus a
-// running FMNMX3.
+// inside a y block, so it moves into the row's threshold.  The element loop does not even form L_ij:
+// it bounds a whole 32-column group G by  c max_{j in G} acc_ij + min_{j in G} |y_j|^2 (1 - 2^-21)  (c < 0),
+// one FMNMX3 per two pairs, and only a group that reaches the threshold is read again column by column.
+// The database chunk is packed in the order of |y_j|^2 (api.cu), which makes the group bound as good as the
+// per-column one and the per-block margin (max_j' |y_j'|) local; `col_map` translates a packed position
+// back to the caller's row where an index leaves the kernel.
 //
 // Every coarse value is also an UPPER bound of a real pair's distance (value + margin), so a row's
 // bound tightens (atomic min on aux[i].x) whenever one of its candidates is found: 2.3 candidates per
@@ -52,6 +56,7 @@ constexpr int SC_B_KB_BYTES   = TC_BN * 64;  // one k-block of the y block:     
 constexpr int SC_MAX_KB       = 4;           // k <= 128
 constexpr int SC_MAX_STAGES   = 8;
 constexpr int SC_EPI_WARPS    = 16;
+constexpr int SC_BLK          = 64;           // candidate-list slots an epilogue warp reserves at a time
 #ifndef SC_SETS
 #define SC_SETS 1
 #endif
@@ -60,8 +65,16 @@ constexpr int SC_MMA2_WARP    = 2 + SC_EPI_WARPS;  // second MMA issuer (the fir
 constexpr int SC_THREADS      = 96 + 32 * SC_EPI_WARPS;
 constexpr size_t SC_A_RING    = 160 * 1024;
 constexpr size_t SC_SMEM_OPERANDS = (size_t)SC_MAX_KB * SC_B_KB_BYTES + SC_A_RING;  // 224 KB
-constexpr size_t SC_SMEM_BYTES    = SC_SMEM_OPERANDS + TC_BN * 4 + 32 + 256;
+constexpr size_t SC_SMEM_BYTES    = SC_SMEM_OPERANDS + TC_BN * 4 + 96 + 256;
 static_assert(SC_SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA limit");
+
+#ifdef SC_TRACE
+__device__ long long g_sc_trace[8][4096];
+__device__ long long g_sc_wtrace[3][16][2048];   // per epilogue warp: tfull seen, arrive, hit flag
+#define SC_STAMP(EV, TT) do { if (blockIdx.x == 0 && (TT) < 4096u) g_sc_trace[EV][TT] = clock64(); } while (0)
+#else
+#define SC_STAMP(EV, TT) do { } while (0)
+#endif
 
 struct ScreenParams {
   int64_t m, n;
@@ -76,30 +89,29 @@ struct ScreenParams {
   const float* xsc;       // [m] per-row scale of x (prep.cuh; 1 unless the row took its own exponent)
   const unsigned* nonuni; // [2] some row of x / y has its own exponent (y: fused_nn_keys sends everything to the exact kernel)
   float2* aux;            // [m] (U_i - |x_i|^2 rounded up, -|x_i|); the bound tightens as candidates are found
-  int2* cand;             // candidate (row, column) list ...
-  unsigned* cand_cnt;     // ... its fill counter ...
+  int2* cand;             // candidate (row, packed column position) list; (-1, -1) = unused slot ...
+  unsigned* cand_cnt;     // ... its slot counter ([0]; [6] counts the candidates themselves) ...
   unsigned cand_cap;      // ... capacity ...
   unsigned* overflow;     // ... and overflow flag (then the exact pass re-runs)
   const unsigned* run_flag;  // non-null: the whole launch is a no-op unless *run_flag != 0
+  const int* col_map;     // non-null: packed column j is source row col_map[j] (norm-sorted chunk)
   int unit_norm;          // cosine family: rows are unit vectors, d = 1 + acc * c (c without the factor 2)
 };
 
-// 16 columns of this thread's row: lower bounds folded into four running minima (no branches: the
-// eight fragments of a tile overlap in the instruction stream)
-#define B2D_SCREEN_FRAGMENT(R, CBASE)                                                                   \
+// 16 columns of this thread's row folded into four running maxima of the RAW accumulator (no branches, no column
+// terms: the fragments of a tile overlap in the instruction stream).  c < 0, so for a 32-column group G
+//   min_{j in G} (acc_ij c + t_j)  >=  c max_{j in G} acc_ij + min_{j in G} t_j :
+// one FMNMX3 per two pairs here and one FFMA + compare per group, instead of an FFMA2 + FMNMX3 per two pairs and a
+// broadcast shared-memory read of t_j per pair (those reads were as many shared-memory wavefronts as the tensor
+// core's operand reads: ncu).  The group bound is tight because the host packs the chunk in the
+// order of |y_j|^2, so the t_j of 32 neighbouring columns differ by next to nothing.
+#define B2D_SCREEN_FRAGMENT(R)                                                                          \
   _Pragma("unroll") for (int c = 0; c < 16; c += 8)                                                     \
   {                                                                                                     \
-    const float4 ta = *reinterpret_cast<const float4*>(&col_tb[(CBASE) + c]);                           \
-    const float4 tb = *reinterpret_cast<const float4*>(&col_tb[(CBASE) + c + 4]);                       \
-    float v0, v1, v2, v3, v4, v5, v6, v7;                                                               \
-    unpk(fma2(pk(R[c], R[c + 1]), cf2, pk(ta.x, ta.y)), v0, v1);                                        \
-    unpk(fma2(pk(R[c + 2], R[c + 3]), cf2, pk(ta.z, ta.w)), v2, v3);                                    \
-    unpk(fma2(pk(R[c + 4], R[c + 5]), cf2, pk(tb.x, tb.y)), v4, v5);                                    \
-    unpk(fma2(pk(R[c + 6], R[c + 7]), cf2, pk(tb.z, tb.w)), v6, v7);                                    \
-    m0 = min3(m0, v0, v1);                                                                              \
-    m1 = min3(m1, v2, v3);                                                                              \
-    m2 = min3(m2, v4, v5);                                                                              \
-    m3 = min3(m3, v6, v7);                                                                              \
+    m0 = max3(m0, __uint_as_float(R[c]), __uint_as_float(R[c + 1]));                                    \
+    m1 = max3(m1, __uint_as_float(R[c + 2]), __uint_as_float(R[c + 3]));                                \
+    m2 = max3(m2, __uint_as_float(R[c + 4]), __uint_as_float(R[c + 5]));                                \
+    m3 = max3(m3, __uint_as_float(R[c + 6]), __uint_as_float(R[c + 7]));                                \
   }
 
 __global__ void __launch_bounds__(SC_THREADS, 1)
@@ -113,7 +125,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* a_base  = smem + SC_MAX_KB * SC_B_KB_BYTES;
   float* col_tb    = reinterpret_cast<float*>(smem + SC_SMEM_OPERANDS);  // [256] |y_j|^2 (1 - 2^-21), +inf beyond n
   float* col_ny    = col_tb + TC_BN;                                     // [8] per-warp maxima of the margin factor
-  uint64_t* bars   = reinterpret_cast<uint64_t*>(col_ny + 8);
+  float* col_gm    = col_ny + 8;                                         // [8] per 32-column group: min of col_tb
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(col_gm + 8);
   uint64_t* afull  = bars;                      // [SC_MAX_STAGES]
   uint64_t* aempty = bars + SC_MAX_STAGES;      // [SC_MAX_STAGES]
   uint64_t* bfull  = bars + 2 * SC_MAX_STAGES;  // [1]
@@ -164,10 +177,16 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t s = t_it % n_stages, ph = (t_it / n_stages) & 1;
         ptx::mbar_wait(&aempty[s], ph ^ 1);
         if (ptx::elect_one()) {
+#if defined(SC_EXP) && SC_EXP == 1   // experiment: x tiles loaded only while the ring fills (stale operands afterwards)
+          if (t_it >= n_stages) ptx::mbar_arrive(&afull[s]); else {
+#endif
           ptx::mbar_expect_tx(&afull[s], stage_bytes);
           for (int kb = 0; kb < nkb; ++kb)
             ptx::tma_load_2d(a_base + s * stage_bytes + kb * SC_A_KB_BYTES, &tmap_a, &afull[s], kb * 64, mt * TC_BM,
                              pol);
+#if defined(SC_EXP) && SC_EXP == 1
+          }
+#endif
         }
         __syncwarp();
       }
@@ -206,7 +225,9 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           continue;
         }
         ptx::mbar_wait(&tempty[parity], ((tt >> 1) & 1) ^ 1);
+        if (lane == 0) SC_STAMP(0, tt);
         ptx::mbar_wait(&afull[s], ph);
+        if (lane == 0) SC_STAMP(1, tt);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t da = ptx::umma_desc_sw64(ptx::smem_u32(a_base + s * stage_bytes));
@@ -224,6 +245,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::mma_commit(&aempty[s]);
           if (mt + 2 >= mt1) ptx::mma_commit(bempty);  // our last tile of the item
           ptx::mma_commit(&tfull[parity]);
+          SC_STAMP(2, tt);
         }
         __syncwarp();
       }
@@ -239,6 +261,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const float cf0 = __ldg(p.coef);
     const bool xnu  = __ldg(&p.nonuni[0]) != 0u;
     const float2 aux_none = make_float2(__int_as_float(0xff800000), 0.f);  // rows beyond m: threshold NaN, never taken
+    unsigned blk_base = 0;      // this warp's block of candidate-list slots ...
+    int blk_used      = SC_BLK; // ... and how many of them are taken (SC_BLK: none reserved yet)
     uint32_t t_it = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_s, p.sel_lo, p.sel_hi);
@@ -270,7 +294,10 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nyv = fmaxf(nyv, __shfl_xor_sync(0xffffffffu, nyv, o));
-        if (lane == 0) col_ny[et >> 5] = nyv;
+        float gm = tv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        if (lane == 0) { col_ny[et >> 5] = nyv; col_gm[et >> 5] = gm; }
         col_tb[et] = tv;
       }
       ptx::bar_sync(1, 32 * SC_EPI_WARPS);
@@ -288,7 +315,6 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (mt_own + SC_SETS < mt1 && row + SC_SETS * TC_BM < p.m) aux_nxt = __ldg(&p.aux[row + SC_SETS * TC_BM]);
         // thread == row: a row with its own exponent just has its own coefficient
         const float cf     = (xnu && row < p.m) ? cf0 * __ldg(&p.xsc[row]) : cf0;
-        const uint64_t cf2 = pk(cf, cf);
         // U_i - |x_i|^2 + |x_i| * max margin, nudged up so that it stays an upper bound
         float thr = fmaf(-aux_c.y, ny_max, aux_c.x);
         thr       = thr + fabsf(thr) * (1.f / 4194304.f);
@@ -296,88 +322,159 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t as = tt & 1, aph = (tt >> 1) & 1;
         ptx::mbar_wait(&tfull[as], aph);
         ptx::tc_fence_after();
+#ifdef SC_TRACE
+        if (lane == 0 && blockIdx.x == 0 && tt < 2048u) g_sc_wtrace[0][w][tt] = clock64();
+#endif
+        if (lane == 0 && w == 0) SC_STAMP(3, tt);
+        if (lane == 0 && w == 9) SC_STAMP(7, tt);
+#if defined(SC_EXP) && SC_EXP == 2   // experiment: no epilogue work
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+        continue;
+#endif
         const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * TC_BN + g * SC_CW;
         const int cb          = g * SC_CW;
         uint32_t ra[16], rb[16];
         unsigned hitmask = 0;  // bit gp: some column of the gp-th 32-column group reaches the threshold
         float m0, m1, m2, m3;
-#define B2D_GROUP_BEGIN m0 = m1 = m2 = m3 = __int_as_float(0x7f800000);
-#define B2D_GROUP_END(GP) hitmask |= (fminf(min3(m0, m1, m2), m3) <= thr) ? (1u << (GP)) : 0u;
+#define B2D_GROUP_BEGIN m0 = m1 = m2 = m3 = __int_as_float(0xff800000);
+#define B2D_GROUP_END(GP) hitmask |= (fmaf(fmaxf(max3(m0, m1, m2), m3), cf, col_gm[(cb >> 5) + (GP)]) <= thr) ? (1u << (GP)) : 0u;
         ptx::tmem_ld_32x16(t_base, ra);
 #pragma unroll
         for (int gp = 0; gp < SC_CW / 32; ++gp) {  // two register buffers: the next load is in flight during the math
           ptx::tmem_ld_wait();
           ptx::tmem_ld_32x16(t_base + 32 * gp + 16, rb);
           B2D_GROUP_BEGIN
-          B2D_SCREEN_FRAGMENT(ra, cb + 32 * gp)
+          B2D_SCREEN_FRAGMENT(ra)
           ptx::tmem_ld_wait();
           if (gp + 1 < SC_CW / 32) ptx::tmem_ld_32x16(t_base + 32 * gp + 32, ra);
-          B2D_SCREEN_FRAGMENT(rb, cb + 32 * gp + 16)
+          B2D_SCREEN_FRAGMENT(rb)
           B2D_GROUP_END(gp)
         }
 #undef B2D_GROUP_BEGIN
 #undef B2D_GROUP_END
-        unsigned long long cmask = 0ull;  // columns of this row (bit = column - cb) that go to the exact pass
+        if (lane == 0 && w == 0) SC_STAMP(4, tt);
+        unsigned long long cmask[SC_SETS] = {};  // columns of this row (bit = column - cb) that go to the exact pass
         float vmin = __int_as_float(0x7f800000);
-        if (__any_sync(0xffffffffu, hitmask != 0u)) {
-          // rare (a per cent or two of the warp-tiles): some column of some row of this warp can still
-          // hold the minimum.  The accumulator is still ours: read the 32-column groups concerned again
-          // and note every column whose lower bound reaches the threshold.
+        const bool any_hit = __any_sync(0xffffffffu, hitmask != 0u);
+        if (any_hit) {
+          // 8-9 % of the warp-tiles on the benchmark's data in the first chunk, a fraction of a per cent later: some
+          // column of some row of this warp can still hold the minimum.  The accumulator is still ours: a group
+          // that hit is read again (both halves in flight together) and looked at column by column.  (Doing this on
+          // the spot per fragment, from the registers of the main pass, costs a vote and a branch per fragment on
+          // EVERY warp-tile: measured slower as soon as hits are rare, i.e. for every chunk but the first.)
 #pragma unroll 1
           for (int gp = 0; gp < SC_CW / 32; ++gp) {
             const bool mine = (hitmask >> gp) & 1u;
             if (!__any_sync(0xffffffffu, mine)) continue;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = 32 * gp + 16 * h;
-              ptx::tmem_ld_32x16(t_base + c0, ra);
-              ptx::tmem_ld_wait();
-              if (mine) {
-                unsigned bits = 0;
+            ptx::tmem_ld_32x16(t_base + 32 * gp, ra);
+            ptx::tmem_ld_32x16(t_base + 32 * gp + 16, rb);
+            ptx::tmem_ld_wait();
+            if (mine) {
+              // (the instruction count is what this path costs -- one warp's share of the issue slots: 32 x (FFMA,
+              // compare, predicated OR) plus a min3 tree; the smallest value of the group is a candidate whenever any is)
+              const float* tb = &col_tb[cb + 32 * gp];
+              const float thr_f = fminf(thr, 3.0e38f);   // +inf columns (beyond n) never pass, even against an infinite bound
+              float lv[32];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                  const float lv = fmaf(__uint_as_float(ra[c]), cf, col_tb[cb + c0 + c]);
-                  if (lv <= thr && lv < __int_as_float(0x7f800000)) {
-                    bits |= 1u << c;
-                    vmin = fminf(vmin, lv);
-                  }
-                }
-                cmask |= static_cast<unsigned long long>(bits) << c0;
+              for (int c = 0; c < 16; ++c) {
+                lv[c]      = fmaf(__uint_as_float(ra[c]), cf, tb[c]);
+                lv[16 + c] = fmaf(__uint_as_float(rb[c]), cf, tb[16 + c]);
               }
+              unsigned bits = 0;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) bits |= (lv[c] <= thr_f) ? (1u << c) : 0u;
+              float g0 = min3(lv[0], lv[1], lv[2]), g1 = min3(lv[3], lv[4], lv[5]), g2 = min3(lv[6], lv[7], lv[8]),
+                    g3 = min3(lv[9], lv[10], lv[11]);
+#pragma unroll
+              for (int c = 12; c < 32; c += 8) {
+                g0 = min3(g0, lv[c], lv[c + 1]);
+                g1 = min3(g1, lv[c + 2], lv[c + 3]);
+                if (c + 4 < 32) g2 = min3(g2, lv[c + 4], lv[c + 5]);
+                if (c + 6 < 32) g3 = min3(g3, lv[c + 6], lv[c + 7]);
+              }
+              if (bits != 0u) vmin = fminf(vmin, fminf(min3(g0, g1, g2), g3));
+              cmask[gp >> 1] |= static_cast<unsigned long long>(bits) << (32 * (gp & 1));
             }
           }
         }
         // hand the accumulator back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
+#ifdef SC_TRACE
+        { const bool hit = __any_sync(0xffffffffu, any_hit);
+          if (lane == 0 && blockIdx.x == 0 && tt < 2048u) { g_sc_wtrace[1][w][tt] = clock64(); g_sc_wtrace[2][w][tt] = hit ? 1 : 0; } }
+#endif
+        if (lane == 0 && w == 0) SC_STAMP(5, tt);
+        if (lane == 0 && w == 15) SC_STAMP(6, tt);
         if (lane == 0) ptx::mbar_arrive(&tempty[as]);
-        if (cmask != 0ull) {
-          // every coarse value is also an UPPER bound of a real pair's distance (value + margin): later
-          // tiles of this row, here and on the other SMs, screen against the tighter bound
-          float nb = fmaf(-aux_c.y, ny_max, vmin);
-          nb += (fabsf(nb) + 2.f * (aux_c.y * aux_c.y + yn_max)) * (1.f / 2097152.f);
-          if (nb < aux_c.x) {
-            int* addr = reinterpret_cast<int*>(&p.aux[row].x);
-            int old   = __float_as_int(aux_c.x);
-            while (nb < __int_as_float(old)) {
-              const int seen = atomicCAS(addr, old, __float_as_int(nb));
-              if (seen == old) break;
-              old = seen;
+        // Nothing below may make this warp late for its next tile (the accumulator stage is free again only when
+        // all 16 warps have drained it): the timeline showed warps arriving 1000-3000 cycles late after an
+        // atomicCAS round trip on the bound plus one same-address atomicAdd per candidate.  So: the bound is lowered
+        // with a fire-and-forget reduction (no return value), and list slots come out of a private block of SC_BLK
+        // entries per warp, reserved with ONE atomicAdd when the previous block is used up (unused entries of a
+        // block are marked invalid, nn_exact_kernel skips them); the entry holds the packed POSITION, which
+        // nn_exact_kernel translates (a dependent col_map load here would stall the store).
+        int ncand = 0;
+#pragma unroll
+        for (int wd = 0; wd < SC_SETS; ++wd) ncand += __popcll(cmask[wd]);
+        if (__any_sync(0xffffffffu, ncand != 0)) {
+          if (ncand != 0) {
+            // every coarse value is also an UPPER bound of a real pair's distance (value + margin): later
+            // tiles of this row, here and on the other SMs, screen against the tighter bound
+            float nb = fmaf(-aux_c.y, ny_max, vmin);
+            nb += (fabsf(nb) + 2.f * (aux_c.y * aux_c.y + yn_max)) * (1.f / 2097152.f);
+            if (nb < aux_c.x) {   // float min as integer reductions: non-negative -> signed min, negative -> unsigned max
+              if (nb >= 0.f) atomicMin(reinterpret_cast<int*>(&p.aux[row].x), __float_as_int(nb));
+              else atomicMax(reinterpret_cast<unsigned*>(&p.aux[row].x), __float_as_uint(nb));
             }
           }
-          while (cmask != 0ull) {
-            const int c = __ffsll(static_cast<long long>(cmask)) - 1;
-            cmask &= cmask - 1ull;
-            const unsigned slot = atomicAdd(p.cand_cnt, 1u);
-            if (slot < p.cand_cap)
-              p.cand[slot] = make_int2(static_cast<int>(row), n_blk * TC_BN + cb + c);
-            else
-              *p.overflow = 1u;
+          int incl = ncand;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          if (lane == 0) atomicAdd(p.cand_cnt + 6, static_cast<unsigned>(total));   // real candidates (slots include unused ones)
+          unsigned slot;
+          if (total > SC_BLK) {  // (more candidates in one warp-tile than a block holds: a reservation of its own)
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(p.cand_cnt, static_cast<unsigned>(total));
+            slot = __shfl_sync(0xffffffffu, base, 0) + static_cast<unsigned>(incl - ncand);
+          } else {
+            if (blk_used + total > SC_BLK) {
+#pragma unroll 1
+              for (int i = blk_used + lane; i < SC_BLK; i += 32)
+                if (blk_base + i < p.cand_cap) p.cand[blk_base + i] = make_int2(-1, -1);
+              unsigned base = 0;
+              if (lane == 0) base = atomicAdd(p.cand_cnt, static_cast<unsigned>(SC_BLK));
+              blk_base = __shfl_sync(0xffffffffu, base, 0);
+              blk_used = 0;
+            }
+            slot = blk_base + static_cast<unsigned>(blk_used + incl - ncand);
+            blk_used += total;
+          }
+#pragma unroll
+          for (int wd = 0; wd < SC_SETS; ++wd) {
+            unsigned long long cm = cmask[wd];
+#pragma unroll 1
+            while (cm != 0ull) {
+              const int c = __ffsll(static_cast<long long>(cm)) - 1 + 64 * wd;
+              cm &= cm - 1ull;
+              if (slot < p.cand_cap) p.cand[slot] = make_int2(static_cast<int>(row), n_blk * TC_BN + cb + c);
+              else *p.overflow = 1u;
+              ++slot;
+            }
           }
         }
       }
       t_it += static_cast<uint32_t>(mt1 - mt0);
     }
+#pragma unroll 1
+    for (int i = blk_used + lane; i < SC_BLK; i += 32)   // the unused rest of this warp's last block
+      if (blk_base + i < p.cand_cap) p.cand[blk_base + i] = make_int2(-1, -1);
   }
 
   ptx::tc_fence_before();
