@@ -138,7 +138,9 @@ struct TcWorkspace {
   unsigned* gmax;  // [2]
   float* coef;     // [1]
   unsigned* has_lo;  // [1]
-  float2* aux;       // [m]    screened NN: per-row (bound - |x|^2, -|x|)
+  float4* aux;       // [m]    screened NN: per-row (bound - |x|^2, |x|, |x - hi part|, -)
+  float* xlo;        // [m]    screened NN: |x_i - hi part| (prep.cuh lvec)
+  float* ylo;        // [n]
   int2* cand;        // [cap]  screened NN: candidate list
   unsigned* cand_cnt;  // [1] (+ overflow flag right behind it)
   unsigned cand_cap;
@@ -177,7 +179,7 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
   // (+2^19: the coarse kernel's warps take list slots in blocks of 64 -- 148 x 16 warps x 2 launches leave up to
   // ~300k slots unused, which must not look like an overflow when m is small)
   w.cand_cap = with_keys ? static_cast<unsigned>(std::min<int64_t>(128 * m + (1 << 19), 0x7fffffff)) : 0u;
-  w.aux      = reinterpret_cast<float2*>(c + take(with_keys ? static_cast<size_t>(m) * 8 : 0));
+  w.aux      = reinterpret_cast<float4*>(c + take(with_keys ? static_cast<size_t>(m) * 16 : 0));
   w.cand_cnt = reinterpret_cast<unsigned*>(c + take(with_keys ? 32 : 0));
   w.cand     = reinterpret_cast<int2*>(c + take(static_cast<size_t>(w.cand_cap) * 8));
   w.yt   = reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4));
@@ -190,6 +192,8 @@ static TcWorkspace tc_layout(void* base, int64_t m, int64_t n, int64_t k, bool w
     w.sort_val[i] = reinterpret_cast<int*>(c + take(ns * 4));
   }
   w.sort_tmp = c + take(with_keys ? kSortTmpBytes : 0);
+  w.xlo = with_keys ? reinterpret_cast<float*>(c + take(static_cast<size_t>(m) * 4)) : nullptr;
+  w.ylo = with_keys ? reinterpret_cast<float*>(c + take(static_cast<size_t>(n) * 4)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -215,8 +219,8 @@ static int launch_prep(cudaStream_t s, const TcWorkspace& w, const void* x, int6
                        const int* y_gather = nullptr)
 {
   PrepParams p;
-  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, w.xsc, xn, nullptr};
-  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, w.ysc, yn, y_gather};
+  p.side[0] = PrepSide{x, xrs, xcs, m, w.xop, w.xt, w.xsc, xn, w.xlo, nullptr};
+  p.side[1] = PrepSide{y, yrs, ycs, n, w.yop, w.yt, w.ysc, yn, w.ylo, y_gather};
   p.k = static_cast<int>(k); p.nkb = static_cast<int>((k + 31) / 32); p.mode = mode; p.center = center;
   p.gmax = w.gmax; p.coef = w.coef; p.has_lo = w.has_lo; p.nonuni = w.nonuni;
   p.xform = xform; p.coef_mul = coef_mul; p.tx_const = tx_const;
@@ -417,7 +421,7 @@ static int launch_screen(cudaStream_t s, const TcWorkspace& w, int64_t m, int64_
   p.chunks_m = (p.tiles_m + p.chunk - 1) / p.chunk;
   p.n_items  = static_cast<int64_t>(p.tiles_sel) * p.chunks_m;
   p.xsc = w.xsc; p.nonuni = w.nonuni;
-  p.yt = w.yt; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
+  p.yt = w.yt; p.ylo = w.ylo; p.coef = w.coef; p.aux = w.aux; p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.cand_cap = w.cand_cap;
   p.overflow = overflow; p.run_flag = run_flag; p.unit_norm = unit_norm; p.col_map = col_map;
   if (p.n_items == 0) return B2D_OK;
   CUtensorMap ma, mb;
@@ -851,7 +855,7 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   p.sel_s = kSel; p.sel_lo = 0; p.sel_hi = 1;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
-  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt,
+  nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt, w.xlo,
                                                                          w.cand, flags, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
   rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr, unit_norm, col_map);

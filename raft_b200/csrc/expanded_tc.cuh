@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(256) nn_sortkey_kernel(const float* y, int64_t
 }
 
 // after the exact sub-sampled pass: thr = incumbent distance, incumbent -> candidate, keys reset
-__global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, int2* cand, unsigned* flags,
+__global__ void nn_seed_kernel(long long* keys, float4* aux, const float* xt, const float* xlo, int2* cand, unsigned* flags,
                                int64_t m, int64_t n, int64_t idx_offset)
 {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -930,7 +930,7 @@ __global__ void nn_seed_kernel(long long* keys, float2* aux, const float* xt, in
   }
   // screening compares v = d - |x|^2 with (bound - |x|^2), rounded up so that it stays an upper bound
   const float xn = xt[i];
-  aux[i]  = make_float2((t - xn) + (t + xn) * (1.f / 2097152.f), -sqrtf(xn));
+  aux[i]  = make_float4((t - xn) + (t + xn) * (1.f / 2097152.f), sqrtf(xn) * (1.f + 1.f / 4194304.f), xlo[i], 0.f);
   cand[i] = c;
 }
 

@@ -40,6 +40,8 @@ struct PrepSide {
   float* tvec;      // [rows]
   float* svec;      // [rows] 2^(E - e_row): 1 for every row that shares the matrix exponent E (see prep_split_kernel)
   const float* ext_norm_sq;  // optional caller-provided squared norms (fusedL2NN xn/yn)
+  float* lvec;               // optional [rows]: |row - hi part| in the units of the (normalised) row: what the 1-product
+                             // coarse pass of the screened NN search leaves out (screen_tc.cuh)
   const int* gather;         // optional: packed row r is source row gather[r] (norm-sorted database of the screened NN search)
 };
 
@@ -171,11 +173,14 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   __half* orow   = sd.op + r * static_cast<int64_t>(p.nkb) * 64;
   const int kpad = p.nkb * 32;
   bool any_lo    = false;
+  float res2     = 0.f;   // sum of (xs - hi)^2: the part of the row the hi half does not carry
   for (int t = lane; t < kpad; t += 32) {
     float xs = 0.f;
     if (t < p.k) xs = (ld_elem(row + t * sd.cs, p.xform) - mean) * scale;
     const __half h = __float2half_rn(xs);
-    const __half l = __float2half_rn(xs - __half2float(h));
+    const float rs = xs - __half2float(h);   // exact in fp32
+    const __half l = __float2half_rn(rs);
+    res2 = fmaf(rs, rs, res2);
     any_lo |= (__half2float(l) != 0.f);
     const int b = t >> 5, j = t & 31;
     orow[b * 64 + j]      = h;
@@ -185,6 +190,12 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepParams p)
   // kernel then runs one product instead of three
   if (__any_sync(0xffffffffu, any_lo) && lane == 0 && *reinterpret_cast<volatile unsigned*>(p.has_lo) == 0u)
     atomicExch(p.has_lo, 1u);
+  if (sd.lvec != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
+    // back to the units of the row (2^-e_row; the cosine scale already holds 1 / |row|), rounded up
+    if (lane == 0) sd.lvec[r] = ldexpf(sqrtf(res2) * (1.f + 1.f / 65536.f), -e_row);
+  }
   if (lane == 0) {
     float t;
     if (p.mode == PREP_L2 || p.mode == PREP_INNER_NORM) t = sd.ext_norm_sq ? sd.ext_norm_sq[rsrc] : static_cast<float>(ss);

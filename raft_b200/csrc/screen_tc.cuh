@@ -4,11 +4,11 @@
 // leaves each x row with an upper bound U_i of its minimum.  This kernel visits the other blocks with
 // ONE tensor product per k-block (hi*hi only: a third of the exact kernel's MMA work, half of its
 // operand bytes) and computes, per pair, a rigorous LOWER bound of the fp32-grade distance
-//     L_ij = acc_ij * c + |y_j|^2 (1 - 2^-21) - 1.05 * 2^-9 |x_i| max_j' |y_j'|     (j' over the y block)
-// (cosine / correlation: rows are unit vectors after prep, d = 1 + acc * c, margin 1.05 * 2^-10)
-// (dropped cross terms: at most 2^-10 (1 + 2^-11) |x||y| in the dot product, i.e. 2^-9.. after the
-// factor 2; the remaining 5% of the margin and the 2^-21 |y|^2 cover the fp32 rounding of the
-// epilogue).  Only pairs with L_ij <= U_i can hold the minimum: they go to a candidate list that
+//     L_ij = acc_ij * c + |y_j|^2 (1 - 2^-21) - margin_i,
+//     margin_i = f (|x_i| YL + |xl_i| Y + 3 |xl_i| YL) + f 0.05 * 2^-10 |x_i| Y      (Y, YL: block maxima of |y_j|, |yl_j|)
+// where xl = x - (its hi part) is MEASURED per row by prep.cuh and f = 2 (L2) or 1 (cosine / correlation: rows are
+// unit vectors after prep, d = 1 + acc * c): Cauchy-Schwarz on the three dropped products; the last term and the
+// 2^-21 |y|^2 cover the fp32 rounding of the accumulation and of the epilogue.  Only pairs with L_ij <= U_i can hold the minimum: they go to a candidate list that
 // nn_exact_kernel re-measures straight from the fp32 inputs.  The margin is a per-row constant
 // inside a y block, so it moves into the row's threshold.  The element loop does not even form L_ij:
 // it bounds a whole 32-column group G by  c max_{j in G} acc_ij + min_{j in G} |y_j|^2 (1 - 2^-21)  (c < 0),
@@ -88,7 +88,8 @@ struct ScreenParams {
   const float* coef;      // [1] -2 * 2^-(ex+ey)
   const float* xsc;       // [m] per-row scale of x (prep.cuh; 1 unless the row took its own exponent)
   const unsigned* nonuni; // [2] some row of x / y has its own exponent (y: fused_nn_keys sends everything to the exact kernel)
-  float2* aux;            // [m] (U_i - |x_i|^2 rounded up, -|x_i|); the bound tightens as candidates are found
+  const float* ylo;       // [n] |y_j - hi part| (prep.cuh lvec)
+  float4* aux;            // [m] (U_i - |x_i|^2 rounded up, |x_i|, |x_i - hi part|, -); the bound tightens as candidates are found
   int2* cand;             // candidate (row, packed column position) list; (-1, -1) = unused slot ...
   unsigned* cand_cnt;     // ... its slot counter ([0]; [6] counts the candidates themselves) ...
   unsigned cand_cap;      // ... capacity ...
@@ -124,9 +125,10 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* b_base  = smem;
   uint8_t* a_base  = smem + SC_MAX_KB * SC_B_KB_BYTES;
   float* col_tb    = reinterpret_cast<float*>(smem + SC_SMEM_OPERANDS);  // [256] |y_j|^2 (1 - 2^-21), +inf beyond n
-  float* col_ny    = col_tb + TC_BN;                                     // [8] per-warp maxima of the margin factor
+  float* col_ny    = col_tb + TC_BN;                                     // [8] per-warp maxima of |y_j|
   float* col_gm    = col_ny + 8;                                         // [8] per 32-column group: min of col_tb
-  uint64_t* bars   = reinterpret_cast<uint64_t*>(col_gm + 8);
+  float* col_nl    = col_gm + 8;                                         // [8] per-warp maxima of |y_j - hi part|
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(col_nl + 8);
   uint64_t* afull  = bars;                      // [SC_MAX_STAGES]
   uint64_t* aempty = bars + SC_MAX_STAGES;      // [SC_MAX_STAGES]
   uint64_t* bfull  = bars + 2 * SC_MAX_STAGES;  // [1]
@@ -260,7 +262,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int et  = threadIdx.x - 64;
     const float cf0 = __ldg(p.coef);
     const bool xnu  = __ldg(&p.nonuni[0]) != 0u;
-    const float2 aux_none = make_float2(__int_as_float(0xff800000), 0.f);  // rows beyond m: threshold NaN, never taken
+    const float4 aux_none = make_float4(__int_as_float(0xff800000), 0.f, 0.f, 0.f);  // rows beyond m: threshold -inf, never taken
     unsigned blk_base = 0;      // this warp's block of candidate-list slots ...
     int blk_used      = SC_BLK; // ... and how many of them are taken (SC_BLK: none reserved yet)
     uint32_t t_it = 0;
@@ -272,7 +274,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // this warp's first tile of the item, and its row data (global-load latency hides behind the
       // column-term barrier below)
       int mt_own = SC_SETS == 2 ? mt0 + ((set ^ static_cast<int>(t_it)) & 1) : mt0;
-      float2 aux_nxt = aux_none;
+      float4 aux_nxt = aux_none;
       {
         const int64_t r = static_cast<int64_t>(mt_own) * TC_BM + q * 32 + lane;
         if (mt_own < mt1 && r < p.m) aux_nxt = __ldg(&p.aux[r]);
@@ -281,42 +283,57 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::bar_sync(1, 32 * SC_EPI_WARPS);
       if (et < TC_BN) {
         const int64_t gj = static_cast<int64_t>(n_blk) * TC_BN + et;
-        float tv = __int_as_float(0x7f800000), nyv = 0.f;  // +inf: never a candidate
+        float tv = __int_as_float(0x7f800000), nyv = 0.f, nlv = 0.f;  // +inf: never a candidate
         if (gj < p.n) {
-          if (p.unit_norm) {  // |y_j| = 1 and no factor 2 in c: margin 1.05 * 2^-10, column term 0
+          nlv = __ldg(&p.ylo[gj]);
+          if (p.unit_norm) {  // |y_j| = 1, column term 0
             tv  = 0.f;
-            nyv = 1.05f / 1024.f;
+            nyv = 1.f;
           } else {
             tv  = __ldg(&p.yt[gj]);
-            nyv = sqrtf(tv) * (1.05f / 512.f);
+            nyv = sqrtf(tv) * (1.f + 1.f / 4194304.f);
             tv  = tv - tv * (1.f / 2097152.f);
           }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nyv = fmaxf(nyv, __shfl_xor_sync(0xffffffffu, nyv, o));
+        for (int o = 16; o > 0; o >>= 1) {
+          nyv = fmaxf(nyv, __shfl_xor_sync(0xffffffffu, nyv, o));
+          nlv = fmaxf(nlv, __shfl_xor_sync(0xffffffffu, nlv, o));
+        }
         float gm = tv;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gm = fminf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-        if (lane == 0) { col_ny[et >> 5] = nyv; col_gm[et >> 5] = gm; }
+        if (lane == 0) { col_ny[et >> 5] = nyv; col_nl[et >> 5] = nlv; col_gm[et >> 5] = gm; }
         col_tb[et] = tv;
       }
       ptx::bar_sync(1, 32 * SC_EPI_WARPS);
-      float ny_max = 0.f;
+      // What the coarse product leaves out of <x, y>:  xh.yl + xl.yh + xl.yl  with x = xh + xl (hi part + the rest), so by
+      // Cauchy-Schwarz at most |x| |yl| + |xl| |y| + 3 |xl| |yl|; the residual norms are MEASURED per row by prep.cuh
+      // (about 0.2 * 2^-10 of the row norm for fp16 rounding, against the worst case 2^-11 per element that the first
+      // version of this bound assumed: the margin, and with it the number of candidates it lets through, drops to ~45 %).
+      // With Y = max |y_j|, YL = max |yl_j| over the block and f = 2 (L2: d = .. - 2 <x, y>) or 1 (cosine family):
+      //   margin_i = |x_i| P + |xl_i| Q,   P = f (YL + 0.05 * 2^-10 Y),   Q = f (Y + 3 YL)
+      // (the 0.05 * 2^-10 |x| |y| term covers the fp32 rounding of the accumulation and of the epilogue, as before).
+      float y_max = 0.f, yl_max = 0.f;
 #pragma unroll
-      for (int i = 0; i < TC_BN / 32; ++i) ny_max = fmaxf(ny_max, col_ny[i]);
-      const float yn_max = p.unit_norm ? 1.f : (ny_max * (512.f / 1.05f)) * (ny_max * (512.f / 1.05f));  // max |y_j|^2 of the block
+      for (int i = 0; i < TC_BN / 32; ++i) { y_max = fmaxf(y_max, col_ny[i]); yl_max = fmaxf(yl_max, col_nl[i]); }
+      const float ff     = p.unit_norm ? 1.f : 2.f;
+      const float marg_p = ff * fmaf(y_max, 0.05f / 1024.f, yl_max) * (1.f + 1.f / 1048576.f);
+      const float marg_q = ff * fmaf(3.f, yl_max, y_max) * (1.f + 1.f / 1048576.f);
+      const float yn_max = y_max * y_max;  // max |y_j|^2 of the block
 
       const uint32_t t_item0 = t_it;
       for (; mt_own < mt1; mt_own += SC_SETS) {
         const uint32_t tt   = t_item0 + static_cast<uint32_t>(mt_own - mt0);  // global tile counter of this tile
         const int64_t row   = static_cast<int64_t>(mt_own) * TC_BM + q * 32 + lane;
-        const float2 aux_c  = aux_nxt;
+        const float4 aux_c  = aux_nxt;
         aux_nxt             = aux_none;
         if (mt_own + SC_SETS < mt1 && row + SC_SETS * TC_BM < p.m) aux_nxt = __ldg(&p.aux[row + SC_SETS * TC_BM]);
         // thread == row: a row with its own exponent just has its own coefficient
         const float cf     = (xnu && row < p.m) ? cf0 * __ldg(&p.xsc[row]) : cf0;
-        // U_i - |x_i|^2 + |x_i| * max margin, nudged up so that it stays an upper bound
-        float thr = fmaf(-aux_c.y, ny_max, aux_c.x);
+        // U_i - |x_i|^2 + margin_i, nudged up so that it stays an upper bound
+        const float margin = fmaf(aux_c.y, marg_p, aux_c.z * marg_q);
+        float thr = aux_c.x + margin;
         thr       = thr + fabsf(thr) * (1.f / 4194304.f);
 
         const uint32_t as = tt & 1, aph = (tt >> 1) & 1;
@@ -423,7 +440,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (ncand != 0) {
             // every coarse value is also an UPPER bound of a real pair's distance (value + margin): later
             // tiles of this row, here and on the other SMs, screen against the tighter bound
-            float nb = fmaf(-aux_c.y, ny_max, vmin);
+            float nb = vmin + margin;
             nb += (fabsf(nb) + 2.f * (aux_c.y * aux_c.y + yn_max)) * (1.f / 2097152.f);
             if (nb < aux_c.x) {   // float min as integer reductions: non-negative -> signed min, negative -> unsigned max
               if (nb >= 0.f) atomicMin(reinterpret_cast<int*>(&p.aux[row].x), __float_as_int(nb));
