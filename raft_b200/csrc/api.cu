@@ -839,30 +839,33 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   if (!screen) return launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
 
   // Screened search (screen_tc.cuh).  With S = 32 and r = index of a 256-row y block modulo S:
-  //   A  exact arg-min kernel on the blocks r == 0            -> every row has an upper bound
-  //   T  coarse 1-product screen on the blocks r == 1 (trial) -> candidates, tighter bounds
-  //      decide on the device: few candidates per row -> screening pays, go on with it; many (data
-  //      whose norms dwarf the nearest-neighbour distances, e.g. far-from-origin clusters: the
-  //      screen's margin is relative to |x||y|) -> the remaining blocks take the exact kernel
-  //   R  coarse screen on the blocks r >= 2                   (if screening pays)
+  //   A  exact arg-min kernel on the blocks r == 0            -> every row has an upper bound U_i
+  //   T  coarse 1-product screen on the SAME blocks (trial)   -> the incumbent again and everything within the margin
+  //      of it.  Two jobs: (1) A chooses among near-ties (1e-5 relative) with tensor arithmetic and keeps one column;
+  //      the others must reach the exact re-evaluation like any candidate of the other blocks, or the result is only
+  //      as good as A's arithmetic; (2) the number of candidates per row is the measure of whether screening pays:
+  //      many (data whose norms dwarf the nearest-neighbour distances: the margin is relative to |x||y|) -> the
+  //      remaining blocks take the exact kernel
+  //   R  coarse screen on the blocks r >= 1                   (if screening pays)
   //   E  exact re-evaluation of every candidate, straight from the fp32 inputs
-  //   X  exact kernel on r == 1 / r >= 2                      (only where candidates were dropped, or
-  //                                                            where screening was called off)
+  //   X  exact kernel on r >= 1                               (only where candidates were dropped -- list overflow --
+  //                                                            or where screening was called off)
   // Every launch after T is conditional on a device flag: no host round trip, no wrong answer.
   constexpr int kSel = 32;
   const float tau = g_nn_tau.load(std::memory_order_relaxed);
-  unsigned* flags = w.cand_cnt;  // [0] count [1] overflow [2] go_screen [3] go_exact [4] redo_trial [5] count after T
+  unsigned* flags = w.cand_cnt;  // [0] slots [1] overflow [2] go_screen [3] go_exact [4] - [5] candidates after T [6] candidates
   p.sel_s = kSel; p.sel_lo = 0; p.sel_hi = 1;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
   nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt, w.xlo,
                                                                          w.cand, flags, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, 1, 2, flags + 1, nullptr, unit_norm, col_map);
+  rc = launch_screen(s, w, m, n, k, kSel, 0, 1, flags + 1, nullptr, unit_norm, col_map);
   if (rc) return rc;
-  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 1, w.nonuni);
+  // (tau + 1: the trial finds every row's incumbent again)
+  nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau + 1.f, 1, w.nonuni);
   B2D_CUDA(cudaGetLastError());
-  rc = launch_screen(s, w, m, n, k, kSel, 2, kSel, flags + 1, flags + 2, unit_norm, col_map);
+  rc = launch_screen(s, w, m, n, k, kSel, 1, kSel, flags + 1, flags + 2, unit_norm, col_map);
   if (rc) return rc;
   nn_decide_kernel<<<1, 1, 0, s>>>(flags, static_cast<unsigned>(m), tau, 2, w.nonuni);
   B2D_CUDA(cudaGetLastError());
@@ -872,10 +875,7 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
                                           ldy, static_cast<int>(k), idx_offset, unit_norm, center, static_cast<unsigned>(m), col_map);
   B2D_CUDA(cudaGetLastError());
-  p.sel_lo = 1; p.sel_hi = 2; p.run_flag = flags + 4;
-  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
-  if (rc) return rc;
-  p.sel_lo = 2; p.sel_hi = kSel; p.run_flag = flags + 3;
+  p.sel_lo = 1; p.sel_hi = kSel; p.run_flag = flags + 3;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
   return B2D_OK;

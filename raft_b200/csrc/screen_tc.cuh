@@ -226,10 +226,10 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::mbar_wait(&afull[s], ph);
           continue;
         }
+        ptx::mbar_wait(&afull[s], ph);   // (the operands arrive long before the accumulator is free: off the critical path)
+        if (lane == 0) SC_STAMP(1, tt);
         ptx::mbar_wait(&tempty[parity], ((tt >> 1) & 1) ^ 1);
         if (lane == 0) SC_STAMP(0, tt);
-        ptx::mbar_wait(&afull[s], ph);
-        if (lane == 0) SC_STAMP(1, tt);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t da = ptx::umma_desc_sw64(ptx::smem_u32(a_base + s * stage_bytes));

@@ -28,5 +28,24 @@ print("silhouette", silhouette_score(r(500, 16), lab, 4))
 from raft_b200.stats import trustworthiness_score
 xx = r(600, 20)
 print("trustworthiness", trustworthiness_score(xx, xx[:, :3].contiguous(), n_neighbors=7))
+# round 2: k <= 64 store path (3-D TMA map), 2-CTA kernel, per-row exponents, fp64, ratio metrics, BrayCurtis, argmin,
+# kNN overflow repair (database ordered by decreasing distance)
+d = pairwise_distance(r(256, 64), r(512, 64), metric="sqeuclidean")
+from raft_b200 import _lib
+_lib.lib().b2d_set_option(b"pairwise_2cta", 1.0)
+d = pairwise_distance(r(384, 128), r(768, 128), metric="sqeuclidean")
+_lib.lib().b2d_set_option(b"pairwise_2cta", 0.0)
+xo = r(300, 96); xo[7] *= 1e-9; xo[9] *= 1e6
+d = pairwise_distance(xo, r(260, 96), metric="sqeuclidean")
+d = pairwise_distance(r(70, 33).double(), r(90, 33).double(), metric="correlation")
+b = (r(200, 40) > 0).float()
+d = pairwise_distance(b, (r(130, 40) > 0).float(), metric="jaccard")
+d = pairwise_distance(r(130, 33).abs(), r(70, 33).abs(), metric="braycurtis")
+from raft_b200.matrix import argmin
+print("argmin", int(argmin(r(300, 777)).sum()))
+q = r(64, 32); base = r(5000, 32)
+order = torch.argsort(torch.cdist(q[:1], base)[0], descending=True)
+dd, ii = brute_force.knn(base[order].contiguous(), q, k=16)
+print("knn ordered", int(ii.sum()))
 torch.cuda.synchronize()
 print("done")
