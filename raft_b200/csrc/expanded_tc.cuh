@@ -68,6 +68,14 @@ constexpr int TC_EPI_WARPS   = 8;
 constexpr int TC_THREADS     = 64 + 32 * TC_EPI_WARPS;
 
 enum TcEpilogue : int { EPI_STORE = 0, EPI_MINLOC = 1, EPI_TOPK = 2 };
+// max(v, 0) that keeps a NaN (fmaxf(NaN, 0) = 0 would turn a poisoned distance into a perfect match)
+__device__ __forceinline__ float clamp0(float v)
+{
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 enum TcPost : int { POST_NONE = 0, POST_CLAMP = 1, POST_CLAMP_SQRT = 2,
                     POST_JACCARD = 3,  // d = 1 - a / (s - a), a = <x,y>, s = |x|^2 + |y|^2 (0/0 -> 0): direct-store path only
                     POST_DICE    = 4 };  // d = 1 - 2 a / s
@@ -78,7 +86,7 @@ __device__ __forceinline__ float post_ratio(float a, float s)
 {
   const float den = kPost == POST_JACCARD ? s - a : s;
   const float num = kPost == POST_JACCARD ? a : 2.f * a;
-  return den > 0.f ? fmaxf(1.f - __fdividef(num, den), 0.f) : 0.f;
+  return !(den <= 0.f) ? clamp0(1.f - __fdividef(num, den)) : 0.f;   // (NaN inputs give NaN, 0/0 gives 0)
 }
 
 struct TcParams {
@@ -448,7 +456,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               }
               if (kPost != POST_NONE) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+                for (int c = 0; c < 32; ++c) v[c] = clamp0(v[c]);
                 if (p.diag_zero && gi >= gj && gi < gj + 128) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
@@ -537,7 +545,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int64_t gj0 = static_cast<int64_t>(n_blk) * TC_BN + cbase;
             if (kPost != POST_NONE) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+              for (int c = 0; c < 32; ++c) v[c] = clamp0(v[c]);
               if (p.diag_zero && gi >= gj0 && gi < gj0 + 32) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
@@ -709,7 +717,7 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
             if (kPost != POST_NONE && kPost < POST_JACCARD && (p.acc_mode == 0 || p.acc_mode == 3)) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+              for (int c = 0; c < 32; ++c) v[c] = clamp0(v[c]);
               if (p.diag_zero) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

@@ -133,8 +133,8 @@ __device__ __forceinline__ void t2_emit(const uint32_t (&r0)[32], const uint32_t
     float x0, x1;
     unpk(fma2(a, cf_rr, add2(ta_rr, tb2[i])), x0, x1);
     if (kPost != POST_NONE) {
-      x0 = fmaxf(x0, 0.f);
-      x1 = fmaxf(x1, 0.f);
+      x0 = clamp0(x0);
+      x1 = clamp0(x1);
       if (!kFast && diag_zero) {
         if (gi == gj + 8 * i) x0 = 0.f;
         if (gi == gj + 8 * i + 1) x1 = 0.f;
