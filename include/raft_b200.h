@@ -91,7 +91,7 @@ int b2d_version(void);
 int b2d_set_option(const char* name, double value);
 /* Diagnostic -- SYNCHRONISES `stream`: control words of the last screened fusedL2NN chunk in `workspace`:
  * [0] list slots in use (one incumbent per row + the blocks of 64 the screen reserved), [1] list overflow, [2] go_screen,
- * [3] go_exact, [4] redo_trial, [5] candidates after the trial pass, [6] candidates found by the screen.  `out7`: 7 words. */
+ * [3] go_exact, [4] (unused), [5] candidates after the trial pass, [6] candidates found by the screen.  `out7`: 7 words. */
 int b2d_debug_nn_stats(void* stream, const void* workspace, int64_t m, int64_t n, int64_t k, unsigned* out7);
 /* thread-local description of the last non-zero status returned on this thread */
 const char* b2d_last_error(void);
@@ -131,9 +131,10 @@ int b2d_fused_distance_nn(void* stream, b2d_kvp_if* out, int metric, const float
  * init_keys == 0 continues from the keys an earlier call or another GPU left (they also serve as
  * starting bounds of the screened search, so exchanging keys early makes the rest of a shard
  * cheaper -- INTEGRATION.md section 3).  b2d_fused_l2_nn_finalize unpacks (clamp at 0, optional sqrt).
- * For 64 < k <= 128 and n >= 16384 the result is produced by a screened search (exact tensor pass
- * on 1/32 of y, 1-product lower-bound screen on the rest, exact fp32 re-evaluation of the
- * candidates, device-side fallback to the exact pass): same answer, about a third of the work. */
+ * For 64 < k <= 128 and n >= 16384 the result is produced by a screened search (y worked through in norm-ordered
+ * chunks of 2^20 rows: exact tensor pass on 1/32 of a chunk, 1-product lower-bound screen on all of it, exact fp32
+ * re-evaluation of the candidates, device-side fallback to the exact pass): same answer, about a third of the
+ * work.  Row indices in the keys are always the caller's (source) rows. */
 int b2d_fused_l2_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ldx, const float* y,
                          int64_t ldy, const float* xn, const float* yn, int64_t m, int64_t n,
                          int64_t k, int64_t idx_offset, int init_keys, void* workspace,

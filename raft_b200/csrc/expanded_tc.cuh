@@ -886,11 +886,11 @@ __global__ void minloc_finalize_kernel(KvpIF* out, const long long* keys, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Screened fusedL2NN (64 < k <= 128, large n): an exact pass over every 32nd y block gives each row an
-// upper bound of its minimum; the coarse pass of screen_tc.cuh (1 tensor product instead of 3)
-// keeps only the columns whose rigorous LOWER bound reaches that upper bound; those few are
-// re-evaluated exactly, straight from the fp32 inputs (sum (x-y)^2), together with the incumbent,
-// so every finalist is measured with the same arithmetic.
+// Screened fusedL2NN (64 < k <= 128, large n; orchestration: fused_nn_keys_chunk in api.cu).  The chunk of y is packed
+// in the order of its squared row norms; an exact pass over every 32nd block gives each row an upper bound of its
+// minimum; the coarse pass of screen_tc.cuh (1 tensor product instead of 3) over ALL blocks keeps only the columns
+// whose rigorous LOWER bound reaches that upper bound; those few are re-evaluated exactly, straight from the fp32
+// inputs (sum (x-y)^2), together with the incumbent, so every finalist is measured with the same arithmetic.
 
 // sort key of a database row: the bits of its squared norm (fp32, non-negative: the unsigned order is the float order)
 __global__ void __launch_bounds__(256) nn_sortkey_kernel(const float* y, int64_t ldy, int64_t n, int k, const float* yn,
