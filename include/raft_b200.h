@@ -66,7 +66,8 @@ enum {
   B2D_BrayCurtis          = 14, /* sum |x - y| / sum |x + y| */
   B2D_JensenShannon       = 15,
   B2D_HammingUnexpanded   = 16,
-  B2D_KLDivergence        = 17,
+  B2D_KLDivergence        = 17, /* 0.5 sum x log(x / y), 0 log 0 = 0; +inf where y = 0 < x (the mathematical value; pinned by
+                                   tests/golden); operand roles follow (x, y) of the call in row- AND column-major order */
   B2D_RusselRaoExpanded   = 18,
   B2D_DiceExpanded        = 19  /* 1 - 2 <x,y> / (|x|^2 + |y|^2): Dice dissimilarity on indicator data */
 };
