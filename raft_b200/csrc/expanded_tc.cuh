@@ -202,6 +202,29 @@ __device__ __forceinline__ float max3(float a, float b, float c)
   return r;
 }
 
+// EPI_TOPK slow path (one row of one fragment: 16 values, columns col0 + 8 i + e): every value at or below the row's
+// k-th best so far takes a slot of the row's list; a full list keeps the smallest dropped key (knn_merge_kernel decides
+// from it whether the row must be repaired).  Deliberately NOT inlined, see the call site.
+__device__ __noinline__ void knn_append16(unsigned* cnt, long long* cand, unsigned cap, long long* dropmin, int64_t row,
+                                          long long col0, float xn, float thr, float a0, float a1, float a2, float a3,
+                                          float a4, float a5, float a6, float a7, float a8, float a9, float a10, float a11,
+                                          float a12, float a13, float a14, float a15)
+{
+  const float a[16] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15};
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float lv = a[t];
+    const float dv = lv + xn;
+    if (dv <= thr && lv < __int_as_float(0x7f800000)) {
+      const long long gj  = col0 + 8 * (t >> 1) + (t & 1);
+      const long long key = (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
+      const unsigned slot = atomicAdd(&cnt[row], 1u);
+      if (slot < cap) cand[row * cap + slot] = key;
+      else atomicMin(&dropmin[row], key);   // list full (ordered / adversarial data): remember the best key that was dropped
+    }
+  }
+}
+
 template <bool kResident, int kEpi, int kPost, bool kTma>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -804,24 +827,14 @@ expanded_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     atomicMin(&p.keys[row0 + 8 * j], key);
                     thr[j] = dv;
                   } else {
-                    // EPI_TOPK: everything at or below the row's k-th best so far goes to the row's list
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                      for (int e = 0; e < 2; ++e) {
-                        const float lv = v[4 * i + o + e];
-                        const float dv = lv + xnr[j];
-                        if (dv <= thr[j] && lv < inf) {
-                          const int64_t row   = row0 + 8 * j;
-                          const unsigned slot = atomicAdd(&p.knn_cnt[row], 1u);
-                          const long long gj  = static_cast<long long>(n_blk) * TC_BN + cl0 + 8 * i + e + p.idx_offset;
-                          if (slot < p.knn_cap)
-                            p.knn_cand[row * p.knn_cap + slot] =
-                              (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll);
-                          else  // list full (ordered / adversarial data): remember the best key that was dropped
-                            atomicMin(&p.knn_dropmin[row], (static_cast<long long>(ordered_bits(dv)) << 32) | (gj & 0xFFFFFFFFll));
-                        }
-                      }
+                    // EPI_TOPK: everything at or below the row's k-th best so far goes to the row's list.  ONE copy of that
+                    // code: unrolled into the 8 (fragment, row) sites of the tile loop it made this instantiation ~50 KB
+                    // larger than the instruction cache holds -- ncu: 61 % of the stall samples "no instruction", issue slots
+                    // 6 % busy, the passes at a fifth of the arg-min kernel's rate.
+                    knn_append16(p.knn_cnt, p.knn_cand, p.knn_cap, p.knn_dropmin, row0 + 8 * j,
+                                 static_cast<long long>(n_blk) * TC_BN + cl0 + p.idx_offset, xnr[j], thr[j], v[o], v[o + 1],
+                                 v[4 + o], v[4 + o + 1], v[8 + o], v[8 + o + 1], v[12 + o], v[12 + o + 1], v[16 + o], v[16 + o + 1],
+                                 v[20 + o], v[20 + o + 1], v[24 + o], v[24 + o + 1], v[28 + o], v[28 + o + 1]);
                   }
                 }
               }
