@@ -1074,16 +1074,20 @@ __global__ void __launch_bounds__(256) knn_merge_kernel(long long* topk, const l
   const unsigned nc   = min(craw, static_cast<unsigned>(KNN_CAP));
   if (nc == 0u) return;  // nothing new for this row (the common case in the late passes)
   long long* b = buf[wid];
-  for (int t = lane; t < KNN_SORT; t += 32) {
+  // sort only as much as there is (warp-uniform): with k = 16 and ~16 new entries per pass that is 32 or 64 keys,
+  // not KNN_SORT = 256 -- the merge launches were a third of a 100000 x 100000 kNN
+  int ssz = 32;
+  while (ssz < kk + static_cast<int>(nc)) ssz <<= 1;
+  for (int t = lane; t < ssz; t += 32) {
     long long key = 0x7FFFFFFFFFFFFFFFll;
     if (t < kk) key = topk[row * kk + t];
     else if (t - kk < static_cast<int>(nc)) key = cand[row * KNN_CAP + (t - kk)];
     b[t] = key;
   }
   __syncwarp();
-  for (int size = 2; size <= KNN_SORT; size <<= 1)
+  for (int size = 2; size <= ssz; size <<= 1)
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < KNN_SORT / 2; t += 32) {
+      for (int t = lane; t < ssz / 2; t += 32) {
         const int i = 2 * t - (t & (stride - 1)), j = i + stride;
         const bool up = (i & size) == 0;
         const long long a = b[i], c = b[j];
