@@ -804,7 +804,7 @@ size_t b2d_fused_l2_nn_workspace_bytes(int64_t m, int64_t n, int64_t k)
 // one chunk of y (prep + search); keys carry the result so far (and act as the rows' bounds)
 static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, int64_t ldx, const float* y, int64_t ldy,
                                const float* xn, const float* yn, int64_t m, int64_t n, int64_t k, int64_t idx_offset,
-                               void* workspace, int mode, int center, bool allow_screen)
+                               void* workspace, int mode, int center, bool allow_screen, bool have_bounds)
 {
   TcWorkspace w = tc_layout(workspace, m, n, k, true);
   const int nkb = static_cast<int>((k + 31) / 32);
@@ -854,9 +854,15 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   constexpr int kSel = 32;
   const float tau = g_nn_tau.load(std::memory_order_relaxed);
   unsigned* flags = w.cand_cnt;  // [0] slots [1] overflow [2] go_screen [3] go_exact [4] - [5] candidates after T [6] candidates
+  // `have_bounds`: the keys already carry every row's best over earlier chunks / shards (a later chunk of this call, or
+  // a call that continues from exchanged keys).  A sample of this chunk would add next to nothing to such a bound, so A
+  // is skipped -- T and R then cover every block, and so does X if it has to run.  (Correct for ANY keys: a row
+  // without a finite bound makes everything a candidate, the list overflows and X takes over; only slower.)
   p.sel_s = kSel; p.sel_lo = 0; p.sel_hi = 1;
-  rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
-  if (rc) return rc;
+  if (!have_bounds) {
+    rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
+    if (rc) return rc;
+  }
   nn_seed_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.aux, w.xt, w.xlo,
                                                                          w.cand, flags, m, n, idx_offset);
   B2D_CUDA(cudaGetLastError());
@@ -875,7 +881,7 @@ static int fused_nn_keys_chunk(cudaStream_t s, int64_t* keys, const float* x, in
   nn_exact_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<long long*>(keys), w.cand, w.cand_cnt, w.cand_cap, x, ldx, y,
                                           ldy, static_cast<int>(k), idx_offset, unit_norm, center, static_cast<unsigned>(m), col_map);
   B2D_CUDA(cudaGetLastError());
-  p.sel_lo = 1; p.sel_hi = kSel; p.run_flag = flags + 3;
+  p.sel_lo = have_bounds ? 0 : 1; p.sel_hi = kSel; p.run_flag = flags + 3;
   rc = launch_tc(s, w, p, k, EPI_MINLOC, POST_NONE);
   if (rc) return rc;
   return B2D_OK;
@@ -907,11 +913,12 @@ static int fused_nn_keys(void* stream, int64_t* keys, const float* x, int64_t ld
   const bool screen_ok = (mode == PREP_L2 || mode == PREP_COSINE) && nkb_all >= 3 && nkb_all <= TC_MAX_RES_KB && !screen_off;
   constexpr int64_t kChunkRows = kNnChunkRows;
   if (!screen_ok || n <= kChunkRows)
-    return fused_nn_keys_chunk(s, keys, x, ldx, y, ldy, xn, yn, m, n, k, idx_offset, workspace, mode, center, screen_ok);
+    return fused_nn_keys_chunk(s, keys, x, ldx, y, ldy, xn, yn, m, n, k, idx_offset, workspace, mode, center, screen_ok,
+                               init_keys == 0);
   for (int64_t off = 0; off < n; off += kChunkRows) {
     const int64_t nc = std::min<int64_t>(kChunkRows, n - off);
     int rc = fused_nn_keys_chunk(s, keys, x, ldx, y + off * ldy, ldy, xn, yn ? yn + off : nullptr, m, nc, k,
-                                 idx_offset + off, workspace, mode, center, true);
+                                 idx_offset + off, workspace, mode, center, true, init_keys == 0 || off > 0);
     if (rc) return rc;
   }
   return B2D_OK;
