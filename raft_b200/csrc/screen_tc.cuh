@@ -265,6 +265,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const float4 aux_none = make_float4(__int_as_float(0xff800000), 0.f, 0.f, 0.f);  // rows beyond m: threshold -inf, never taken
     unsigned blk_base = 0;      // this warp's block of candidate-list slots ...
     int blk_used      = SC_BLK; // ... and how many of them are taken (SC_BLK: none reserved yet)
+    bool list_full    = false;  // a reservation of this warp came back beyond the list's capacity (sticky, warp-uniform)
     uint32_t t_it = 0;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n_blk = sel_to_blk(static_cast<int>(item % p.tiles_sel), p.sel_s, p.sel_lo, p.sel_hi);
@@ -447,42 +448,52 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               else atomicMax(reinterpret_cast<unsigned*>(&p.aux[row].x), __float_as_uint(nb));
             }
           }
-          int incl = ncand;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
-          if (lane == 0) atomicAdd(p.cand_cnt + 6, static_cast<unsigned>(total));   // real candidates (slots include unused ones)
-          unsigned slot;
-          if (total > SC_BLK) {  // (more candidates in one warp-tile than a block holds: a reservation of its own)
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(p.cand_cnt, static_cast<unsigned>(total));
-            slot = __shfl_sync(0xffffffffu, base, 0) + static_cast<unsigned>(incl - ncand);
+          if (list_full) {
+            // (warp-uniform) a reservation of this warp already came back beyond the end of the list: the overflow flag
+            // is up, the exact pass will redo these blocks, and the slot counter must not keep growing -- data on which
+            // everything is a candidate would otherwise wrap it around and overwrite the incumbents' entries
+            if (lane == 0) *p.overflow = 1u;
           } else {
-            if (blk_used + total > SC_BLK) {
-#pragma unroll 1
-              for (int i = blk_used + lane; i < SC_BLK; i += 32)
-                if (blk_base + i < p.cand_cap) p.cand[blk_base + i] = make_int2(-1, -1);
-              unsigned base = 0;
-              if (lane == 0) base = atomicAdd(p.cand_cnt, static_cast<unsigned>(SC_BLK));
-              blk_base = __shfl_sync(0xffffffffu, base, 0);
-              blk_used = 0;
-            }
-            slot = blk_base + static_cast<unsigned>(blk_used + incl - ncand);
-            blk_used += total;
-          }
+            int incl = ncand;
 #pragma unroll
-          for (int wd = 0; wd < SC_SETS; ++wd) {
-            unsigned long long cm = cmask[wd];
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) atomicAdd(p.cand_cnt + 6, static_cast<unsigned>(total));   // real candidates (slots include unused ones)
+            unsigned slot;
+            if (total > SC_BLK) {  // (more candidates in one warp-tile than a block holds: a reservation of its own)
+              unsigned base = 0;
+              if (lane == 0) base = atomicAdd(p.cand_cnt, static_cast<unsigned>(total));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (base >= p.cand_cap) list_full = true;
+              slot = base + static_cast<unsigned>(incl - ncand);
+            } else {
+              if (blk_used + total > SC_BLK) {
 #pragma unroll 1
-            while (cm != 0ull) {
-              const int c = __ffsll(static_cast<long long>(cm)) - 1 + 64 * wd;
-              cm &= cm - 1ull;
-              if (slot < p.cand_cap) p.cand[slot] = make_int2(static_cast<int>(row), n_blk * TC_BN + cb + c);
-              else *p.overflow = 1u;
-              ++slot;
+                for (int i = blk_used + lane; i < SC_BLK; i += 32)
+                  if (blk_base + i < p.cand_cap) p.cand[blk_base + i] = make_int2(-1, -1);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(p.cand_cnt, static_cast<unsigned>(SC_BLK));
+                blk_base = __shfl_sync(0xffffffffu, base, 0);
+                blk_used = 0;
+                if (blk_base >= p.cand_cap) list_full = true;
+              }
+              slot = blk_base + static_cast<unsigned>(blk_used + incl - ncand);
+              blk_used += total;
+            }
+#pragma unroll
+            for (int wd = 0; wd < SC_SETS; ++wd) {
+              unsigned long long cm = cmask[wd];
+#pragma unroll 1
+              while (cm != 0ull) {
+                const int c = __ffsll(static_cast<long long>(cm)) - 1 + 64 * wd;
+                cm &= cm - 1ull;
+                if (slot < p.cand_cap) p.cand[slot] = make_int2(static_cast<int>(row), n_blk * TC_BN + cb + c);
+                else *p.overflow = 1u;
+                ++slot;
+              }
             }
           }
         }
