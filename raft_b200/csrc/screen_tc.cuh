@@ -179,16 +179,10 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t s = t_it % n_stages, ph = (t_it / n_stages) & 1;
         ptx::mbar_wait(&aempty[s], ph ^ 1);
         if (ptx::elect_one()) {
-#if defined(SC_EXP) && SC_EXP == 1   // experiment: x tiles loaded only while the ring fills (stale operands afterwards)
-          if (t_it >= n_stages) ptx::mbar_arrive(&afull[s]); else {
-#endif
           ptx::mbar_expect_tx(&afull[s], stage_bytes);
           for (int kb = 0; kb < nkb; ++kb)
             ptx::tma_load_2d(a_base + s * stage_bytes + kb * SC_A_KB_BYTES, &tmap_a, &afull[s], kb * 64, mt * TC_BM,
                              pol);
-#if defined(SC_EXP) && SC_EXP == 1
-          }
-#endif
         }
         __syncwarp();
       }
@@ -345,7 +339,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #endif
         if (lane == 0 && w == 0) SC_STAMP(3, tt);
         if (lane == 0 && w == 9) SC_STAMP(7, tt);
-#if defined(SC_EXP) && SC_EXP == 2   // experiment: no epilogue work
+#ifdef SC_NO_EPILOGUE   // diagnostic build: the MMA / TMA side alone
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[as]);
