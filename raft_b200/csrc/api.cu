@@ -105,12 +105,14 @@ struct ProfileRing {
   bool on  = false;
 } g_prof;
 std::mutex g_prof_mu;
+std::atomic<bool> g_prof_armed{false};   // fast path: a call outside a profiling region touches no lock
 
 struct ProfileScope {
   cudaStream_t s;
   int slot = -1;
   explicit ProfileScope(cudaStream_t st) : s(st)
   {
+    if (!g_prof_armed.load(std::memory_order_acquire)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (g_prof.on && 2 * (g_prof.used + 1) <= static_cast<int>(g_prof.ev.size())) {
       slot = g_prof.used++;
@@ -616,6 +618,7 @@ int b2d_profile_begin(int capacity)
   }
   g_prof.used = 0;
   g_prof.on   = true;
+  g_prof_armed.store(true, std::memory_order_release);
   return B2D_OK;
 }
 
@@ -623,6 +626,7 @@ int b2d_profile_end(float* ms, int max_count, int* count)
 {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.on = false;
+  g_prof_armed.store(false, std::memory_order_release);
   if (!ms || !count || max_count < 0) return fail(B2D_ERR_INVALID_ARG, "null ms / count");
   const int c = std::min(g_prof.used, max_count);
   for (int i = 0; i < c; ++i) {
